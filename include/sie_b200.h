@@ -1,0 +1,168 @@
+/*
+ * sie_b200.h -- C ABI of libsie_b200.so: the B200 (sm_100a) implementation of the data-parallel core
+ * of the complex-network + Gaussian-process sea-ice-extent forecaster.
+ *
+ * The reference (William-gregory/SeaIceExtentForecasting) is pure Python and has no FFI; what a
+ * maintainer would bind is its Python call surface.  Each entry point below names the reference
+ * lines whose arithmetic it replaces (paths relative to the reference checkout).  INTEGRATION.md
+ * shows the ctypes stub that sits behind `ComplexNetworks.Network.tau/area_level/intra_links` and
+ * the script-level `detrend/networks/forecast/MLII` helpers.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`; outputs are caller-allocated;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no device sync) unless noted;
+ *   - return value 0 = enqueued OK, negative = argument/launch error (see sie_last_error());
+ *   - per-job data errors (no NaN sentinel cell, fewer than 2 areas, capacity, non-SPD kernel matrix)
+ *     are reported through the per-job `status`/`info` device arrays, mirroring LAPACK `info`;
+ *   - all floating point is FP64, all indices int32; "cell" = flat grid index i*Y+j, "node" = index
+ *     into the ascending list of cells whose series is not identically zero/NaN.
+ *   - jobs: one job = one network build (one field window).  B jobs of the same grid are batched.
+ */
+#ifndef SIE_B200_H
+#define SIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIE_OK 0
+#define SIE_ERR_ARG (-1)          /* bad argument (returned by the call) */
+#define SIE_ERR_LAUNCH (-2)       /* CUDA launch/runtime failure (returned by the call) */
+#define SIE_ERR_UNSUPPORTED (-3)  /* size outside what this build handles */
+
+/* per-job status codes written to device `status[]` arrays */
+#define SIE_JOB_OK 0
+#define SIE_JOB_NO_NAN_CELL 1   /* ComplexNetworks.py:50-51 would raise IndexError */
+#define SIE_JOB_FEW_AREAS 2     /* ComplexNetworks.py:212/:278 would raise ValueError (<2 areas) */
+#define SIE_JOB_CAPACITY 3      /* more areas / nodes than the caller-provided capacity */
+
+int sie_abi_version(void);
+const char* sie_last_error(void);
+/* device facts used by the host layer for launch sizing; returns 0 on success */
+int sie_device_info(int* sm_count, int* max_smem_optin, size_t* l2_bytes);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  per-cell OLS detrend + unit-norm rows + node compaction.
+ * Replaces: detrend()            north/June1st.py:179-194, retro north/retrospective_forecasts/June1st_retro.py:178-195
+ *           node mask + the row centring/scaling inside np.corrcoef   ComplexNetworks.py:32-34, :37
+ *           first-NaN sentinel cell                                   ComplexNetworks.py:50-51
+ * fields      [F][C][Tstride]  input series per cell (NaN = land)
+ * job_field   [B]  which field job b windows;  job_T [B] window length (prefix of the series)
+ * do_detrend  1: remove the OLS line (detrend()), 0: input already detrended (Network(data=dt))
+ * dt          [B][C][Tstride]  residuals (all-NaN for cells with any NaN); may alias nothing; required
+ * trend       [B][C][2] slope,intercept (NaN for cells with any NaN) or NULL
+ * z           [B][ldn][Tp]  unit-norm centred rows, node-compacted, zero padded to Tp (Tp%4==0)
+ * node_cell   [B][ldn], cell_node [B][C] (-1 = not a node), n_nodes [B], first_nan_cell [B] (-1 none)
+ * status      [B] SIE_JOB_CAPACITY if n_nodes > ldn
+ */
+int sie_detrend_zscore(const double* fields, const int32_t* job_field, const int32_t* job_T,
+                       int B, int C, int Tstride, int Tp, int do_detrend,
+                       double* dt, double* trend, double* z,
+                       int32_t* node_cell, int32_t* cell_node, int32_t* n_nodes,
+                       int32_t* first_nan_cell, int32_t* status, int ldn, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  all-pairs Pearson correlation R = Z Z^T on FP64 tensor-core (DMMA m8n8k4) tiles, operands
+ *     staged with bulk async copies (TMA engine) + mbarrier, clip to [-1,1], NaN diagonal, mirrored
+ *     (bitwise symmetric) store, and the significance threshold tau.
+ * Replaces: np.corrcoef + fill_diagonal + t-test + mean      ComplexNetworks.py:34-35, :41-47
+ * r_crit   [B]  host-computed critical correlation: P<alpha  <=>  R > r_crit
+ * R        [B][ldn][ldn] or NULL (tau only; nothing but Z is read and 16 B/tile written)
+ * tile_part [B][max_tiles][2] scratch for deterministic per-tile (sum,count) partials
+ * tau      [B]; tau_sum [B]; tau_cnt [B] (int64)   -- sums are over BOTH triangles like the reference
+ * shard_rank/shard_count: tile-row bi is computed by the rank with bi % shard_count == shard_rank
+ *     (multi-GPU row-block split; tau is then finished by the caller after an all-reduce of sum/cnt).
+ */
+int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32_t* job_T, const double* r_crit,
+                 int B, int ldn, int Tp, double* R,
+                 double* tile_part, size_t tile_part_bytes,
+                 double* tau_sum, int64_t* tau_cnt, double* tau,
+                 int shard_rank, int shard_count, void* stream);
+size_t sie_corr_tau_scratch_bytes(int B, int ldn);
+
+/* K3  local stencil: correlation of every node with its 4 von-Neumann neighbours (up,down,left,right;
+ *     lat-lon wrap in the second axis), NaN where the neighbour is off-grid or not a node.
+ * Replaces: the seed search gathers `corrs[ID,nei]`            ComplexNetworks.py:166-172, :53-78
+ * stencil  [B][ldn][4]
+ */
+int sie_corr_stencil(const double* R, const int32_t* node_cell, const int32_t* cell_node,
+                     const int32_t* n_nodes, int B, int X, int Y, int ldn, int latlon,
+                     double* stencil, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4+K5  tau-thresholded domain growth (step 1) and largest-first merging (step 2); one persistent
+ *        CTA per network, numpy-pairwise-order means so decisions are those of the reference.
+ * Replaces: Network.area_level                                 ComplexNetworks.py:49-278
+ * area_cells [B][C]  member cells, area after area in dict order, each area in its list order
+ * area_start [B][max_areas+1], area_key [B][max_areas] (the reference's dict keys), n_areas [B]
+ * label      [B][C]  index into area_key (dict position) or -1
+ * status     [B]  SIE_JOB_* (areas are still written when status == SIE_JOB_FEW_AREAS, like the
+ *            reference leaves V populated when it raises at :278)
+ * scratch    at least sie_area_level_scratch_bytes(B, X*Y) bytes
+ */
+int sie_area_level(const double* R, const double* stencil, const int32_t* node_cell,
+                   const int32_t* cell_node, const int32_t* n_nodes, const double* tau,
+                   const int32_t* first_nan_cell, int B, int X, int Y, int ldn, int latlon,
+                   int max_areas, int32_t* area_cells, int32_t* area_start, int32_t* area_key,
+                   int32_t* n_areas, int32_t* label, int32_t* status,
+                   void* scratch, size_t scratch_bytes, void* stream);
+size_t sie_area_level_scratch_bytes(int B, int C);
+
+/* ---------------------------------------------------------------------------------------------
+ * K6  area-weighted node series (deterministic row-major segmented sums), population-covariance
+ *     links, strength, strength map.
+ * Replaces: Network.intra_links                                ComplexNetworks.py:283-326
+ * scale      [C]  sqrt(area) or sqrt(cos(lat)) or ones (host computes the square root, :296-301)
+ * anomaly    [B][max_areas][Tstride]; links [B][max_areas][max_areas]; strength [B][max_areas];
+ * strengthmap [B][C] (NaN outside areas)
+ */
+int sie_intra_links(const double* dt, const double* scale, const int32_t* job_T,
+                    const int32_t* area_cells, const int32_t* area_start, const int32_t* n_areas,
+                    const int32_t* label, int B, int C, int Tstride, int max_areas,
+                    double* anomaly, double* links, double* strength, double* strengthmap,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K7-K9  batched GP forecast: predictor selection, optional z-score, graph-Laplacian prior,
+ *        expm (Al-Mohy & Higham scaling-and-squaring Pade, the algorithm behind scipy.linalg.expm),
+ *        Cholesky fit, predictive mean/variance, negative log marginal likelihood (+ MLII gradient).
+ * Replaces: forecast()  north/June1st.py:208-279 (and the 13 sibling scripts), MLII :235-257
+ *
+ * One problem = one (network set, region, hyper-parameter pair).  Problem p reads:
+ *   y            y_all + prob[p].y_off, n = prob[p].n training targets
+ *   predictors   up to two series sets (SIC, SST): set s has n_areas[job_s] series of length n+1 at
+ *                anomaly + (job_s*max_areas + a)*Tstride
+ * and writes out[p] = {fmean, fvar, sigma_f, nlml, g_ell, g_sig, n_pred, expm_m, expm_s, info}.
+ */
+typedef struct SieGpProblem {
+  int32_t job_sic;      /* index into the first anomaly set (required) */
+  int32_t job_sst;      /* index into the second anomaly set, or -1 */
+  int32_t n;            /* training rows; series provide n+1 samples (last = test year) */
+  int32_t y_off;        /* offset of y[0..n) in y_all */
+  int32_t rule;         /* 0: r>0, 1: all, 2: (r>0)&(p/2<alpha) i.e. r > r_sel */
+  int32_t zscore;       /* 1: column z-score over the n+1 rows (June scripts) */
+  int32_t want_grad;    /* 1: also evaluate the MLII gradient */
+  int32_t pad_;
+  double r_sel;         /* critical r for rule 2 (host: beta(n/2-1,n/2-1,-1,2).isf(alpha)) */
+  double ell;           /* l */
+  double sig;           /* sigma_n tilde */
+} SieGpProblem;
+
+typedef struct SieGpResult {
+  double fmean, fvar, sigma_f, nlml, g_ell, g_sig;
+  int32_t n_pred, expm_m, expm_s, info; /* info: 0 ok, k>0 Cholesky failed at pivot k, -1 no predictors, -2 capacity */
+} SieGpResult;
+
+int sie_gp_forecast(const SieGpProblem* prob, int P, const double* y_all,
+                    const double* anom_sic, const int32_t* n_areas_sic, int max_areas_sic, int Tstride_sic,
+                    const double* anom_sst, const int32_t* n_areas_sst, int max_areas_sst, int Tstride_sst,
+                    int max_pred, SieGpResult* out, void* scratch, size_t scratch_bytes, void* stream);
+size_t sie_gp_scratch_bytes(int P, int max_pred, int max_n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIE_B200_H */

@@ -1,0 +1,121 @@
+// Shared helpers for libsie_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/sie_b200.h"
+
+void sie_set_error(const char* fmt, ...);
+
+#define SIE_CHECK_ARG(cond, msg)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      sie_set_error("%s: %s", __func__, msg);    \
+      return SIE_ERR_ARG;                        \
+    }                                            \
+  } while (0)
+
+#define SIE_CHECK_LAUNCH()                                                   \
+  do {                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                    \
+    if (e__ != cudaSuccess) {                                                \
+      sie_set_error("%s: CUDA error %s", __func__, cudaGetErrorString(e__)); \
+      return SIE_ERR_LAUNCH;                                                 \
+    }                                                                        \
+  } while (0)
+
+__device__ __forceinline__ double sie_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// -------------------------------------------------------------------------------------------------
+// numpy pairwise summation (numpy/_core/src/umath/loops_utils.h.src, pairwise_sum_DOUBLE), the order in
+// which `np.sum` / `np.nanmean` add a contiguous 1-D double array:
+//   n < 8     : left-to-right from 0.0
+//   n <= 128  : 8 accumulators r[j]=a[j]; r[j]+=a[i+j] for i=8,16,..<n-n%8;
+//               ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)); then the n%8 tail left-to-right
+//   n > 128   : n2=(n/2)-(n/2)%8;  pairwise(a,n2)+pairwise(a+n2,n-n2)
+// The area-growth and merge decisions of ComplexNetworks.py:113/:250/:252 are float comparisons of such
+// sums, so the device evaluates them in exactly this order.
+//
+// `sie_pw_leaf8`: an aligned group of 8 lanes (lane j = accumulator j) sums one leaf (n <= 128) of a
+// sequence whose i-th element is get(i); NaN entries count as 0 and are tallied in `nan_cnt` (nanmean).
+// All 8 lanes return the same value.
+// -------------------------------------------------------------------------------------------------
+template <typename Get>
+__device__ __forceinline__ double sie_pw_leaf8(Get get, int lo, int n, int j, unsigned gmask, int& nan_cnt) {
+  double res;
+  if (n < 8) {
+    // every lane walks the short list itself (identical values in all lanes)
+    res = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double v = get(lo + i);
+      if (v != v) { v = 0.0; if (j == 0) ++nan_cnt; }
+      res = __dadd_rn(res, v);
+    }
+    return res;
+  }
+  const int nfull = n - (n & 7);
+  double r = get(lo + j);
+  if (r != r) { r = 0.0; ++nan_cnt; }
+  int i = 8;
+  // batches of 4 independent gathers keep several loads in flight per lane
+  for (; i + 24 < nfull; i += 32) {
+    double v0 = get(lo + i + j), v1 = get(lo + i + 8 + j), v2 = get(lo + i + 16 + j), v3 = get(lo + i + 24 + j);
+    if (v0 != v0) { v0 = 0.0; ++nan_cnt; }
+    if (v1 != v1) { v1 = 0.0; ++nan_cnt; }
+    if (v2 != v2) { v2 = 0.0; ++nan_cnt; }
+    if (v3 != v3) { v3 = 0.0; ++nan_cnt; }
+    r = __dadd_rn(r, v0); r = __dadd_rn(r, v1); r = __dadd_rn(r, v2); r = __dadd_rn(r, v3);
+  }
+  for (; i < nfull; i += 8) {
+    double v = get(lo + i + j);
+    if (v != v) { v = 0.0; ++nan_cnt; }
+    r = __dadd_rn(r, v);
+  }
+  // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) : xor-butterfly inside the 8-lane group (IEEE add commutes)
+  r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+  r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));
+  r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+  res = r;
+  for (int t = nfull; t < n; ++t) {
+    double v = get(lo + t);
+    if (v != v) { v = 0.0; if (j == 0) ++nan_cnt; }
+    res = __dadd_rn(res, v);
+  }
+  return res;
+}
+
+// Full pairwise sum of a sequence of length n by one 8-lane group; leaves are visited left to right and
+// combined along the recursion tree with an explicit stack (depth <= 24 covers n < 2^31).
+template <typename Get>
+__device__ __forceinline__ double sie_pw_sum8(Get get, int n, int j, unsigned gmask, int& nan_cnt) {
+  if (n <= 128) return sie_pw_leaf8(get, 0, n, j, gmask, nan_cnt);
+  // iterative post-order walk of pairwise(lo,n) = pairwise(lo,n2) + pairwise(lo+n2,n-n2)
+  int st_lo[24], st_n[24];
+  double st_val[24];
+  unsigned char st_state[24];
+  int sp = 0;
+  st_lo[0] = 0; st_n[0] = n; st_state[0] = 0; sp = 1;
+  double ret = 0.0;
+  while (sp > 0) {
+    int t = sp - 1;
+    if (st_state[t] == 0) {
+      if (st_n[t] <= 128) {
+        ret = sie_pw_leaf8(get, st_lo[t], st_n[t], j, gmask, nan_cnt);
+        --sp;
+      } else {
+        int n2 = st_n[t] / 2; n2 -= n2 % 8;
+        st_state[t] = 1;
+        st_lo[sp] = st_lo[t]; st_n[sp] = n2; st_state[sp] = 0; ++sp;
+      }
+    } else if (st_state[t] == 1) {
+      st_val[t] = ret;
+      int n2 = st_n[t] / 2; n2 -= n2 % 8;
+      st_state[t] = 2;
+      st_lo[sp] = st_lo[t] + n2; st_n[sp] = st_n[t] - n2; st_state[sp] = 0; ++sp;
+    } else {
+      ret = __dadd_rn(st_val[t], ret);
+      --sp;
+    }
+  }
+  return ret;
+}

@@ -1,0 +1,350 @@
+// K2: all-pairs Pearson correlation R = Z Z^T (+ significance threshold tau) and K3: 4-neighbour stencil.
+// Reference: np.corrcoef + fill_diagonal + t-test mean, ComplexNetworks.py:34-35,:41-47; seed-search
+// gathers ComplexNetworks.py:166-172.
+//
+// Z rows are centred and scaled to unit norm by K1, so R_ij is a plain dot product over K = T <= Tp.
+// The contraction runs on the FP64 tensor pipe (mma.sync m8n8k4 -> SASS DMMA.8x8x4; tcgen05 has no f64
+// kind, and ptxas splits the larger sm_90 f64 shapes into 8x8x4 on sm_100a).  A 128-row panel of Z is one
+// contiguous 128*Tp*8-byte run, so operands are staged with 1-D bulk async copies (cp.async.bulk -> SASS
+// UBLKCP, the TMA engine) completing on an mbarrier; Tp = 4 (mod 8) makes the fragment loads
+// bank-conflict free without swizzling.  Persistent CTAs (one per SM) walk the upper-triangular
+// 128x128 tile list with a 2-stage full/empty pipeline; only bi <= bj tiles are computed and results are
+// mirrored, so R is bitwise symmetric like numpy's syrk-based corrcoef.
+// Algorithmic work: N(N+1)T flop per network (upper triangle), 8 N^2 bytes if R is stored.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE = 128;
+constexpr int NWARP = 16;       // 4 x 4 warps, each a 32 x 32 sub-tile = 4 x 4 DMMA blocks
+constexpr int NTHREADS = NWARP * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// per-job tile bookkeeping for this shard: rows bi = rank, rank+count, ... each with (nb - bi) tiles
+__device__ __host__ __forceinline__ long long shard_tiles_before(int q, int nb, int rank, int count) {
+  // tiles in my first q rows
+  return (long long)q * (nb - rank) - (long long)count * q * (q - 1) / 2;
+}
+__device__ __host__ __forceinline__ int shard_rows(int nb, int rank, int count) {
+  return nb > rank ? (nb - rank + count - 1) / count : 0;
+}
+
+__global__ void k_tile_prefix(const int32_t* __restrict__ n_nodes, int B, int ldn, int rank, int count,
+                              long long* __restrict__ prefix) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    long long acc = 0;
+    for (int b = 0; b < B; ++b) {
+      prefix[b] = acc;
+      int N = min(n_nodes[b], ldn);
+      int nb = (N + TILE - 1) / TILE;
+      int rows = shard_rows(nb, rank, count);
+      acc += shard_tiles_before(rows, nb, rank, count);
+    }
+    prefix[B] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_corr_tiles(const double* __restrict__ z, const int32_t* __restrict__ n_nodes,
+             const int32_t* __restrict__ job_T, const double* __restrict__ r_crit,
+             const long long* __restrict__ prefix, int B, int ldn, int Tp, double* __restrict__ R,
+             double* __restrict__ tile_part, int rank, int count) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int panel = TILE * Tp;                       // doubles per panel
+  double* stage_base = reinterpret_cast<double*>(smem_raw);
+  // [stage][A|B][128][Tp]
+  __shared__ uint64_t full_bar[2], empty_bar[2];
+  __shared__ double red_sum[NWARP];
+  __shared__ double red_cnt[NWARP];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = warp >> 2, wc = warp & 3;           // warp position in the 4x4 grid
+  if (tid == 0) {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    mbar_init(&empty_bar[0], NWARP);
+    mbar_init(&empty_bar[1], NWARP);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long total = prefix[B];
+  const uint32_t panel_bytes = (uint32_t)(panel * sizeof(double));
+
+  auto decode = [&](long long item, int& b, int& bi, int& bj) {
+    int lo = 0, hi = B - 1;                          // last b with prefix[b] <= item
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (prefix[mid] <= item) lo = mid; else hi = mid - 1;
+    }
+    b = lo;
+    long long t = item - prefix[b];
+    const int N = min(n_nodes[b], ldn);
+    const int nb = (N + TILE - 1) / TILE;
+    // my row index q: largest q with shard_tiles_before(q) <= t
+    double a = 0.5 * count, bb = (double)(nb - rank) + 0.5 * count;
+    double disc = bb * bb - 4.0 * a * (double)t;
+    int q = (int)((bb - sqrt(disc > 0 ? disc : 0.0)) / (2.0 * a));
+    if (q < 0) q = 0;
+    while (q > 0 && shard_tiles_before(q, nb, rank, count) > t) --q;
+    while (shard_tiles_before(q + 1, nb, rank, count) <= t) ++q;
+    bi = rank + q * count;
+    bj = bi + (int)(t - shard_tiles_before(q, nb, rank, count));
+  };
+
+  auto issue = [&](long long item, int stage) {
+    int b, bi, bj;
+    decode(item, b, bi, bj);
+    double* sA = stage_base + (size_t)stage * 2 * panel;
+    double* sB = sA + panel;
+    const double* gA = z + ((size_t)b * ldn + (size_t)bi * TILE) * Tp;
+    const double* gB = z + ((size_t)b * ldn + (size_t)bj * TILE) * Tp;
+    mbar_expect_tx(&full_bar[stage], 2 * panel_bytes);
+    bulk_g2s(sA, gA, panel_bytes, &full_bar[stage]);
+    bulk_g2s(sB, gB, panel_bytes, &full_bar[stage]);
+  };
+
+  long long item = blockIdx.x;
+  if (item >= total) return;
+  if (tid == 0) issue(item, 0);
+
+  for (int it = 0; item < total; ++it, item += gridDim.x) {
+    const int stage = it & 1;
+    const long long next = item + gridDim.x;
+    if (tid == 0 && next < total) {
+      const int ns = stage ^ 1;
+      if (it >= 1) mbar_wait(&empty_bar[ns], ((it - 1) >> 1) & 1);   // previous user of that stage is done
+      issue(next, ns);
+    }
+    int b, bi, bj;
+    decode(item, b, bi, bj);
+    const int N = min(n_nodes[b], ldn);
+    const int ksteps = (job_T[b] + 3) >> 2;
+    const double rc = r_crit[b];
+
+    mbar_wait(&full_bar[stage], (it >> 1) & 1);
+    const double* sA = stage_base + (size_t)stage * 2 * panel;
+    const double* sB = sA + panel;
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const double* pa = sA + (size_t)(wr * 32 + (lane >> 2)) * Tp + (lane & 3);
+    const double* pb = sB + (size_t)(wc * 32 + (lane >> 2)) * Tp + (lane & 3);
+    for (int ks = 0; ks < ksteps; ++ks) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        af[i] = pa[(size_t)i * 8 * Tp + ks * 4];
+        bf[i] = pb[(size_t)i * 8 * Tp + ks * 4];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);   // smem stage free: the next load overlaps the epilogue
+
+    // ---- epilogue: clip, NaN diagonal, mirrored store, tau partials
+    double lsum = 0.0, lcnt = 0.0;
+    double* Rb = R ? R + (size_t)b * ldn * ldn : nullptr;
+    const bool diag_tile = (bi == bj);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gi = bi * TILE + wr * 32 + i * 8 + (lane >> 2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int gj = bj * TILE + wc * 32 + j * 8 + 2 * (lane & 3);
+        double v0 = acc[i][j][0], v1 = acc[i][j][1];
+        v0 = v0 > 1.0 ? 1.0 : (v0 < -1.0 ? -1.0 : v0);   // np.clip keeps NaN
+        v1 = v1 > 1.0 ? 1.0 : (v1 < -1.0 ? -1.0 : v1);
+        if (gi >= N) continue;
+        const bool in0 = gj < N, in1 = gj + 1 < N;
+        // an element counts when it is strictly above the diagonal; it stands for (i,j) and (j,i)
+        const bool up0 = in0 && (!diag_tile || gj > gi), up1 = in1 && (!diag_tile || gj + 1 > gi);
+        if (up0 && v0 >= 0.0 && v0 > rc) { lsum += v0; lcnt += 1.0; }
+        if (up1 && v1 >= 0.0 && v1 > rc) { lsum += v1; lcnt += 1.0; }
+        if (Rb) {
+          if (diag_tile) {
+            if (in0 && gj == gi) Rb[(size_t)gi * ldn + gj] = sie_nan();
+            if (in1 && gj + 1 == gi) Rb[(size_t)gi * ldn + gj + 1] = sie_nan();
+            if (up0) { Rb[(size_t)gi * ldn + gj] = v0; Rb[(size_t)gj * ldn + gi] = v0; }
+            if (up1) { Rb[(size_t)gi * ldn + gj + 1] = v1; Rb[(size_t)(gj + 1) * ldn + gi] = v1; }
+          } else {
+            if (in1) {
+              *reinterpret_cast<double2*>(Rb + (size_t)gi * ldn + gj) = make_double2(v0, v1);
+              Rb[(size_t)gj * ldn + gi] = v0;
+              Rb[(size_t)(gj + 1) * ldn + gi] = v1;
+            } else if (in0) {
+              Rb[(size_t)gi * ldn + gj] = v0;
+              Rb[(size_t)gj * ldn + gi] = v0;
+            }
+          }
+        }
+      }
+    }
+    // deterministic CTA reduction of the tile partial (fixed shuffle tree, fixed warp order)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+      lcnt += __shfl_xor_sync(0xffffffffu, lcnt, o);
+    }
+    if (lane == 0) { red_sum[warp] = lsum; red_cnt[warp] = lcnt; }
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0, c = 0.0;
+      for (int w = 0; w < NWARP; ++w) { s += red_sum[w]; c += red_cnt[w]; }
+      tile_part[2 * item] = 2.0 * s;       // both triangles
+      tile_part[2 * item + 1] = 2.0 * c;
+    }
+    __syncthreads();
+  }
+}
+
+// one warp per job: fixed-order reduction of the tile partials -> tau_sum, tau_cnt, tau
+__global__ void k_tau_finalize(const double* __restrict__ tile_part, const long long* __restrict__ prefix,
+                               int B, double* __restrict__ tau_sum, int64_t* __restrict__ tau_cnt,
+                               double* __restrict__ tau) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  double s = 0.0, c = 0.0;
+  for (long long i = prefix[b] + lane; i < prefix[b + 1]; i += 32) { s += tile_part[2 * i]; c += tile_part[2 * i + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if (lane == 0) {
+    tau_sum[b] = s;
+    tau_cnt[b] = (int64_t)c;
+    tau[b] = s / c;     // 0/0 -> NaN like np.mean([])
+  }
+}
+
+// K3: one thread per (node, direction)
+__global__ void k_stencil(const double* __restrict__ R, const int32_t* __restrict__ node_cell,
+                          const int32_t* __restrict__ cell_node, const int32_t* __restrict__ n_nodes, int B,
+                          int X, int Y, int ldn, int latlon, double* __restrict__ stencil) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * ldn * 4) return;
+  const int d = (int)(idx & 3);
+  const long long bn = idx >> 2;
+  const int b = (int)(bn / ldn), n = (int)(bn - (long long)b * ldn);
+  double out = sie_nan();
+  const int N = min(n_nodes[b], ldn);
+  if (n < N) {
+    const int c = node_cell[(size_t)b * ldn + n];
+    int i = c / Y, j = c - i * Y;
+    int a = i + (d == 0 ? -1 : (d == 1 ? 1 : 0));
+    int q = j + (d == 2 ? -1 : (d == 3 ? 1 : 0));
+    bool ok = (a >= 0 && a < X);
+    if (q < 0) { if (latlon) q = Y - 1; else ok = false; }
+    if (q >= Y) { if (latlon) q = 0; else ok = false; }
+    if (ok) {
+      const int m = cell_node[(size_t)b * X * Y + a * Y + q];
+      if (m >= 0 && m < N) out = R[(size_t)b * ldn * ldn + (size_t)n * ldn + m];
+    }
+  }
+  stencil[idx] = out;
+}
+
+}  // namespace
+
+extern "C" size_t sie_corr_tau_scratch_bytes(int B, int ldn) {
+  long long nb = (ldn + TILE - 1) / TILE;
+  long long tiles = (long long)B * nb * (nb + 1) / 2;
+  return (size_t)(tiles * 2 * sizeof(double) + (size_t)(B + 1) * sizeof(long long) + 256);
+}
+
+extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32_t* job_T,
+                            const double* r_crit, int B, int ldn, int Tp, double* R, double* tile_part,
+                            size_t tile_part_bytes, double* tau_sum, int64_t* tau_cnt, double* tau,
+                            int shard_rank, int shard_count, void* stream) {
+  SIE_CHECK_ARG(z && n_nodes && job_T && r_crit && tile_part && tau_sum && tau_cnt && tau, "null pointer");
+  SIE_CHECK_ARG(B > 0 && ldn > 0 && (ldn % TILE) == 0, "ldn must be a positive multiple of 128");
+  SIE_CHECK_ARG(Tp >= 4 && (Tp % 4) == 0, "Tp must be a multiple of 4");
+  SIE_CHECK_ARG(shard_count >= 1 && shard_rank >= 0 && shard_rank < shard_count, "bad shard");
+  SIE_CHECK_ARG(tile_part_bytes >= sie_corr_tau_scratch_bytes(B, ldn), "tile_part scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)2 * 2 * TILE * Tp * sizeof(double);
+  int dev = 0, sms = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if ((int)smem + 1024 > max_optin) {
+    sie_set_error("sie_corr_tau: Tp=%d needs %zu B of shared memory (> %d)", Tp, smem, max_optin);
+    return SIE_ERR_UNSUPPORTED;
+  }
+  // scratch layout: [prefix (B+1) int64][pad to 256][tile partials]
+  long long* prefix = reinterpret_cast<long long*>(tile_part);
+  size_t off = (((size_t)(B + 1) * sizeof(long long)) + 255) / 256 * 256;
+  double* parts = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tile_part) + off);
+  k_tile_prefix<<<1, 32, 0, st>>>(n_nodes, B, ldn, shard_rank, shard_count, prefix);
+  SIE_CHECK_LAUNCH();
+  cudaFuncSetAttribute(k_corr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  long long nb = ldn / TILE;
+  long long max_items = (long long)B * nb * (nb + 1) / 2;
+  int grid = (int)(max_items < sms ? max_items : sms);
+  k_corr_tiles<<<grid, NTHREADS, smem, st>>>(z, n_nodes, job_T, r_crit, prefix, B, ldn, Tp, R, parts,
+                                             shard_rank, shard_count);
+  SIE_CHECK_LAUNCH();
+  k_tau_finalize<<<(B + 3) / 4, 128, 0, st>>>(parts, prefix, B, tau_sum, tau_cnt, tau);
+  SIE_CHECK_LAUNCH();
+  return SIE_OK;
+}
+
+extern "C" int sie_corr_stencil(const double* R, const int32_t* node_cell, const int32_t* cell_node,
+                                const int32_t* n_nodes, int B, int X, int Y, int ldn, int latlon,
+                                double* stencil, void* stream) {
+  SIE_CHECK_ARG(R && node_cell && cell_node && n_nodes && stencil, "null pointer");
+  SIE_CHECK_ARG(B > 0 && X > 0 && Y > 0 && ldn > 0, "non-positive size");
+  const long long total = (long long)B * ldn * 4;
+  k_stencil<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(R, node_cell, cell_node, n_nodes,
+                                                                               B, X, Y, ldn, latlon, stencil);
+  SIE_CHECK_LAUNCH();
+  return SIE_OK;
+}

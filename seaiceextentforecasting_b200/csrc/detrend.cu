@@ -1,0 +1,195 @@
+// K1: per-cell OLS detrend, node mask, node compaction and unit-norm rows.
+// Reference: detrend() north/June1st.py:179-194; node mask + np.corrcoef row centring
+// ComplexNetworks.py:32-34,:37; NaN sentinel cell ComplexNetworks.py:50-51.
+//
+// HBM-bound streaming: one warp per (job, cell); lane t walks the series with stride 32 so every warp
+// reads one contiguous T*8-byte run (<= 336 B at T=42) and writes one.  Algorithmic bytes: 16*C*T per
+// window (read raw, write residuals) + 8*N*Tp for the compacted z rows.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_detrend_cells(
+    const double* __restrict__ fields, const int32_t* __restrict__ job_field,
+    const int32_t* __restrict__ job_T, int B, int C, int Tstride, int do_detrend,
+    double* __restrict__ dt, double* __restrict__ trend, int32_t* __restrict__ cell_flag,
+    int32_t* __restrict__ first_nan_cell) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long total = (long long)B * C;
+  if (warp >= total) return;
+  const int b = (int)(warp / C);
+  const int c = (int)(warp - (long long)b * C);
+  const int T = job_T[b];
+  const double* src = fields + ((size_t)job_field[b] * C + c) * Tstride;
+  double* dst = dt + ((size_t)b * C + c) * Tstride;
+
+  // pass 1: NaN census, sum of y
+  double sy = 0.0;
+  int n_nan = 0;
+  for (int t = lane; t < T; t += 32) {
+    double v = src[t];
+    if (v != v) ++n_nan; else sy += v;
+  }
+  n_nan = __reduce_add_sync(0xffffffffu, n_nan);
+  if (n_nan > 0) {
+    // any NaN: linregress propagates NaN through the whole row (all-NaN cells are skipped and stay NaN)
+    if (lane == 0) {
+      atomicMin(first_nan_cell + b, c);
+      cell_flag[(size_t)b * C + c] = 0;
+      if (trend) { trend[((size_t)b * C + c) * 2] = sie_nan(); trend[((size_t)b * C + c) * 2 + 1] = sie_nan(); }
+    }
+    if (do_detrend) {
+      for (int t = lane; t < Tstride; t += 32) dst[t] = sie_nan();
+    } else if (n_nan < T) {
+      // pass-through mode keeps a partially-NaN series visible: it is a node whose correlations are NaN
+      // (np.nanmax ignores the NaNs, np.corrcoef does not) -- ComplexNetworks.py:32-34
+      double mx = -INFINITY;
+      for (int t = lane; t < T; t += 32) { double v = src[t]; if (v == v) mx = fmax(mx, v); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) cell_flag[(size_t)b * C + c] = (fabs(mx) > 0.0) ? 1 : 0;
+    }
+    return;
+  }
+  double mx = -INFINITY;
+  if (do_detrend) {
+    sy = warp_sum(sy);
+    const double ym = sy / (double)T;
+    const double xm = 0.5 * (double)(T - 1);
+    double sxy = 0.0, sxx = 0.0;
+    for (int t = lane; t < T; t += 32) {
+      double dx = (double)t - xm;
+      sxy += dx * (src[t] - ym);
+      sxx += dx * dx;
+    }
+    sxy = warp_sum(sxy) / (double)T;
+    sxx = warp_sum(sxx) / (double)T;
+    const double slope = sxy / sxx;
+    const double icpt = ym - slope * xm;
+    for (int t = lane; t < T; t += 32) {
+      // y - ((slope*t) + intercept): product rounded before the add, like the numpy expression
+      double line = __dadd_rn(__dmul_rn(slope, (double)t), icpt);
+      double r = __dsub_rn(src[t], line);
+      dst[t] = r;
+      mx = fmax(mx, r);
+    }
+    for (int t = T + lane; t < Tstride; t += 32) dst[t] = 0.0;
+    if (trend && lane == 0) {
+      trend[((size_t)b * C + c) * 2] = slope;
+      trend[((size_t)b * C + c) * 2 + 1] = icpt;
+    }
+  } else {
+    for (int t = lane; t < T; t += 32) mx = fmax(mx, src[t]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) cell_flag[(size_t)b * C + c] = (fabs(mx) > 0.0) ? 1 : 0;   // |nanmax| > 0
+}
+
+// One CTA per job: order-preserving compaction of the node flags (ascending flat cell id, :37).
+__global__ void __launch_bounds__(1024) k_compact_nodes(int C, int ldn, int32_t* __restrict__ cell_node,
+                                                        int32_t* __restrict__ node_cell,
+                                                        int32_t* __restrict__ n_nodes,
+                                                        int32_t* __restrict__ first_nan_cell,
+                                                        int32_t* __restrict__ status) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  const int b = blockIdx.x;
+  int32_t* cn = cell_node + (size_t)b * C;
+  int32_t* nc = node_cell + (size_t)b * ldn;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base_s = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+    const int c = c0 + threadIdx.x;
+    const int f = (c < C) ? cn[c] : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, f != 0);
+    const int pre = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[w] = __popc(m);
+    __syncthreads();
+    int off = base_s;
+    for (int i = 0; i < w; ++i) off += warp_tot[i];
+    if (c < C) {
+      if (f) {
+        int idx = off + pre;
+        cn[c] = idx;
+        if (idx < ldn) nc[idx] = c;
+      } else {
+        cn[c] = -1;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += warp_tot[i];
+      base_s += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    n_nodes[b] = base_s;
+    status[b] = (base_s > ldn) ? SIE_JOB_CAPACITY : SIE_JOB_OK;
+    if (first_nan_cell[b] >= C) first_nan_cell[b] = -1;
+  }
+}
+
+// One warp per node: centre, scale to unit norm (np.corrcoef's (x-mean)/sqrt(sum (x-mean)^2)), pad with 0.
+__global__ void __launch_bounds__(256) k_zrows(const double* __restrict__ dt, const int32_t* __restrict__ job_T,
+                                               const int32_t* __restrict__ node_cell,
+                                               const int32_t* __restrict__ n_nodes, int B, int C, int Tstride,
+                                               int Tp, int ldn, double* __restrict__ z) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (warp >= (long long)B * ldn) return;
+  const int b = (int)(warp / ldn);
+  const int n = (int)(warp - (long long)b * ldn);
+  double* zr = z + ((size_t)b * ldn + n) * Tp;
+  const int N = min(n_nodes[b], ldn);
+  if (n >= N) {
+    for (int t = lane; t < Tp; t += 32) zr[t] = 0.0;   // rows past N are zero so padded tiles are harmless
+    return;
+  }
+  const int T = job_T[b];
+  const double* src = dt + ((size_t)b * C + node_cell[(size_t)b * ldn + n]) * Tstride;
+  double s = 0.0;
+  for (int t = lane; t < T; t += 32) s += src[t];
+  const double mean = warp_sum(s) / (double)T;
+  double q = 0.0;
+  for (int t = lane; t < T; t += 32) { double d = src[t] - mean; q += d * d; }
+  const double inv = 1.0 / sqrt(warp_sum(q));
+  for (int t = lane; t < Tp; t += 32) zr[t] = (t < T) ? (src[t] - mean) * inv : 0.0;
+}
+
+}  // namespace
+
+extern "C" int sie_detrend_zscore(const double* fields, const int32_t* job_field, const int32_t* job_T,
+                                  int B, int C, int Tstride, int Tp, int do_detrend, double* dt,
+                                  double* trend, double* z, int32_t* node_cell, int32_t* cell_node,
+                                  int32_t* n_nodes, int32_t* first_nan_cell, int32_t* status, int ldn,
+                                  void* stream) {
+  SIE_CHECK_ARG(fields && job_field && job_T && dt && z && node_cell && cell_node && n_nodes &&
+                    first_nan_cell && status, "null pointer");
+  SIE_CHECK_ARG(B > 0 && C > 0 && Tstride > 0 && ldn > 0, "non-positive size");
+  SIE_CHECK_ARG(Tp >= Tstride && (Tp % 4) == 0, "Tp must be >= Tstride and a multiple of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(first_nan_cell, 0x7f, sizeof(int32_t) * (size_t)B, st);
+  const long long warps = (long long)B * C;
+  const int wpb = 8;
+  k_detrend_cells<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+      fields, job_field, job_T, B, C, Tstride, do_detrend, dt, trend, cell_node, first_nan_cell);
+  SIE_CHECK_LAUNCH();
+  k_compact_nodes<<<B, 1024, 0, st>>>(C, ldn, cell_node, node_cell, n_nodes, first_nan_cell, status);
+  SIE_CHECK_LAUNCH();
+  const long long zwarps = (long long)B * ldn;
+  k_zrows<<<(unsigned)((zwarps + wpb - 1) / wpb), wpb * 32, 0, st>>>(dt, job_T, node_cell, n_nodes, B, C,
+                                                                      Tstride, Tp, ldn, z);
+  SIE_CHECK_LAUNCH();
+  return SIE_OK;
+}

@@ -1,0 +1,699 @@
+// K7-K9: batched GP forecast -- predictor selection, optional z-score, graph-Laplacian prior, expm,
+// Cholesky fit / predict / negative log marginal likelihood (+ MLII gradient).
+// Reference: forecast() north/June1st.py:208-279 (13 sibling scripts differ only in the selection rule and
+// hyper-parameters), nested MLII() north/June1st.py:235-257.
+//
+// One CTA per problem (persistent grid, problems strided).  Np x Np matrices (Np = selected predictors,
+// up to max_pred) live in a per-CTA global scratch slab that stays L2-resident; the n x n kernel matrices
+// (n <= 63 training years) live in shared memory.  expm follows the algorithm scipy.linalg.expm runs
+// (Al-Mohy & Higham 2009: Pade order m in {3,5,7,9,13} chosen from ||A^k||_1 of explicit powers, the
+// exact ||(|A|)^(2m+1)||_1 backward-error check, 2^-s scaling and s squarings; constants and control flow
+// validated against scipy 1.18.1 in tests/test_expm_spec.py), because GP parity at large l*||M|| needs the same
+// (m, s) -- an eigendecomposition would be *more* accurate there but would not match the reference.
+// FP64 FMA work: ~2 Np^3 (6 + s) flop per expm dominates; Cholesky is 2 n^3/3.
+#include "common.cuh"
+
+namespace {
+
+constexpr int GT = 256;          // threads per CTA
+constexpr int MAXN = 64;         // n+1 <= 64 samples
+constexpr int LDS = MAXN + 1;    // padded leading dimension of the shared n x n matrices
+
+__device__ const double kTheta[5] = {1.495585217958292e-002, 2.539398330063230e-001, 9.504178996162932e-001,
+                                     2.097847961257068e+000, 4.25};
+// u * c_m, the backward-error constants of Al-Mohy & Higham (u = 2^-53)
+__device__ const double kCoeff[5] = {1.1102230246251565e-16 * 100800.0, 1.1102230246251565e-16 * 10059033600.0,
+                                     1.1102230246251565e-16 * 4487938430976000.0,
+                                     1.1102230246251565e-16 * 5914384781877411840000.0,
+                                     1.1102230246251565e-16 * 113250775606021113483283660800000000.0};
+__device__ const double kB3[4] = {120., 60., 12., 1.};
+__device__ const double kB5[6] = {30240., 15120., 3360., 420., 30., 1.};
+__device__ const double kB7[8] = {17297280., 8648640., 1995840., 277200., 25200., 1512., 56., 1.};
+__device__ const double kB9[10] = {17643225600., 8821612800., 2075673600., 302702400., 30270240.,
+                                   2162160., 110880., 3960., 90., 1.};
+__device__ const double kB13[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800.,
+                                    129060195264000., 10559470521600., 670442572800., 33522128640., 1323241920.,
+                                    40840800., 960960., 16380., 182., 1.};
+
+struct Smem {
+  double As[16][64 + 2];
+  double Bs[16][64 + 2];
+  double K[MAXN * LDS];     // kernel matrix / Cholesky factor
+  double W[MAXN * LDS];     // X Sigma~ X^T
+  double y[MAXN], ya[MAXN], alpha[MAXN], kxs[MAXN], v[MAXN], xs_tmp[MAXN];
+  double red[GT / 32];
+  int ired[GT / 32];
+  int misc[8];
+  double dmisc[8];
+};
+
+__device__ __forceinline__ double block_sum(double v, Smem& sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+#pragma unroll
+  for (int w = 0; w < GT / 32; ++w) r += sm.red[w];
+  return r;
+}
+__device__ __forceinline__ double block_max(double v, Smem& sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = sm.red[0];
+#pragma unroll
+  for (int w = 1; w < GT / 32; ++w) r = fmax(r, sm.red[w]);
+  return r;
+}
+
+// C[m x n2] = A[m x k] * B[k x n2]; row-major, leading dimensions lda/ldb/ldc; C must not alias A or B.
+__device__ void cta_gemm(double* __restrict__ Cm, int ldc, const double* __restrict__ A, int lda,
+                         const double* __restrict__ Bm, int ldb, int m, int k, int n2, Smem& sm) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int i0 = 0; i0 < m; i0 += 64) {
+    for (int j0 = 0; j0 < n2; j0 += 64) {
+      double acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+      for (int k0 = 0; k0 < k; k0 += 16) {
+        {  // A tile 64 x 16 -> As[kk][row]
+          const int r = tid >> 2, kk = (tid & 3) * 4;
+          const int gr = i0 + r;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int gk = k0 + kk + q;
+            sm.As[kk + q][r] = (gr < m && gk < k) ? A[(size_t)gr * lda + gk] : 0.0;
+          }
+        }
+        {  // B tile 16 x 64 -> Bs[kk][col]
+          const int kk = tid >> 4, c = (tid & 15) * 4;
+          const int gk = k0 + kk;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int gc = j0 + c + q;
+            sm.Bs[kk][c + q] = (gk < k && gc < n2) ? Bm[(size_t)gk * ldb + gc] : 0.0;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+          double a[4], b[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { a[q] = sm.As[kk][ty * 4 + q]; b[q] = sm.Bs[kk][tx * 4 + q]; }
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[p][q] = fma(a[p], b[q], acc[p][q]);
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int gr = i0 + ty * 4 + p;
+        if (gr >= m) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int gc = j0 + tx * 4 + q;
+          if (gc < n2) Cm[(size_t)gr * ldc + gc] = acc[p][q];
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ||A||_1 = max column sum of |A| (Np x Np)
+__device__ double cta_norm1(const double* __restrict__ A, int ld, int np_, Smem& sm) {
+  double best = 0.0;
+  for (int j = threadIdx.x; j < np_; j += GT) {
+    double s = 0.0;
+    for (int i = 0; i < np_; ++i) s += fabs(A[(size_t)i * ld + j]);
+    best = fmax(best, s);
+  }
+  return block_max(best, sm);
+}
+
+// exact || (scale*|A|)^p ||_1 by p transposed mat-vecs on the ones vector (non-negative matrix)
+__device__ double cta_absnorm_power(const double* __restrict__ A, int ld, int np_, double scale, int p,
+                                    double* __restrict__ v0, double* __restrict__ v1, Smem& sm) {
+  for (int j = threadIdx.x; j < np_; j += GT) v0[j] = 1.0;
+  __syncthreads();
+  double* src = v0;
+  double* dst = v1;
+  for (int it = 0; it < p; ++it) {
+    for (int j = threadIdx.x; j < np_; j += GT) {
+      double s = 0.0;
+      for (int i = 0; i < np_; ++i) s = fma(scale * fabs(A[(size_t)i * ld + j]), src[i], s);
+      dst[j] = s;
+    }
+    __syncthreads();
+    double* t = src; src = dst; dst = t;
+  }
+  double best = 0.0;
+  for (int j = threadIdx.x; j < np_; j += GT) best = fmax(best, src[j]);
+  return block_max(best, sm);
+}
+
+__device__ __forceinline__ int ell_of(double t, double normA, int idx, int m) {
+  // lm = max(ceil(log2(t / normA / coeff) / (2m)), 0)
+  if (!(t > 0.0)) return 0;
+  const double val = ceil(log2(t / normA / kCoeff[idx]) / (double)(2 * m));
+  if (val != val) return 1 << 20;
+  if (val > 1.0e6) return 1 << 20;
+  return val > 0.0 ? (int)val : 0;
+}
+
+// dst = c0*I + c1*P1 + c2*P2 + c3*P3 (+ add) ; any pointer may be null
+__device__ void cta_lincomb(double* __restrict__ dst, int ld, int np_, double cI, const double* P1, double c1,
+                            const double* P2, double c2, const double* P3, double c3, const double* add) {
+  for (int idx = threadIdx.x; idx < np_ * np_; idx += GT) {
+    const int i = idx / np_, jj = idx - i * np_;
+    const size_t o = (size_t)i * ld + jj;
+    double v = (i == jj) ? cI : 0.0;
+    if (P1) v += c1 * P1[o];
+    if (P2) v += c2 * P2[o];
+    if (P3) v += c3 * P3[o];
+    if (add) v += add[o];
+    dst[o] = v;
+  }
+  __syncthreads();
+}
+
+// Solve P X = Q in place (X overwrites Q) by Gaussian elimination with partial pivoting; P is destroyed.
+__device__ void cta_lu_solve(double* __restrict__ P, double* __restrict__ Q, int ld, int np_, Smem& sm) {
+  const int tid = threadIdx.x;
+  for (int k = 0; k < np_; ++k) {
+    // pivot search
+    double bv = -1.0; int bi = k;
+    for (int i = k + tid; i < np_; i += GT) {
+      const double a = fabs(P[(size_t)i * ld + k]);
+      if (a > bv) { bv = a; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { sm.red[tid >> 5] = bv; sm.ired[tid >> 5] = bi; }
+    __syncthreads();
+    bv = sm.red[0]; bi = sm.ired[0];
+#pragma unroll
+    for (int w = 1; w < GT / 32; ++w)
+      if (sm.red[w] > bv || (sm.red[w] == bv && sm.ired[w] < bi)) { bv = sm.red[w]; bi = sm.ired[w]; }
+    if (bi != k) {
+      for (int jj = tid; jj < np_; jj += GT) {
+        if (jj >= k) { const double t = P[(size_t)k * ld + jj]; P[(size_t)k * ld + jj] = P[(size_t)bi * ld + jj]; P[(size_t)bi * ld + jj] = t; }
+        const double t2 = Q[(size_t)k * ld + jj]; Q[(size_t)k * ld + jj] = Q[(size_t)bi * ld + jj]; Q[(size_t)bi * ld + jj] = t2;
+      }
+    }
+    __syncthreads();
+    const double piv = P[(size_t)k * ld + k];
+    // eliminate rows below k: row i handled by a group of threads across columns
+    const int rows = np_ - k - 1;
+    const int cols = (np_ - k - 1) + np_;   // trailing columns of P plus all of Q
+    for (int idx = tid; idx < rows * cols; idx += GT) {
+      const int r = idx / cols, c = idx - r * cols;
+      const int i = k + 1 + r;
+      const double l = P[(size_t)i * ld + k] / piv;
+      if (c < np_ - k - 1) {
+        const int jj = k + 1 + c;
+        P[(size_t)i * ld + jj] = fma(-l, P[(size_t)k * ld + jj], P[(size_t)i * ld + jj]);
+      } else {
+        const int jj = c - (np_ - k - 1);
+        Q[(size_t)i * ld + jj] = fma(-l, Q[(size_t)k * ld + jj], Q[(size_t)i * ld + jj]);
+      }
+    }
+    __syncthreads();
+  }
+  // back substitution, one thread per right-hand-side column
+  for (int jj = tid; jj < np_; jj += GT) {
+    for (int i = np_ - 1; i >= 0; --i) {
+      double s = Q[(size_t)i * ld + jj];
+      for (int c = i + 1; c < np_; ++c) s = fma(-P[(size_t)i * ld + c], Q[(size_t)c * ld + jj], s);
+      Q[(size_t)i * ld + jj] = s / P[(size_t)i * ld + i];
+    }
+  }
+  __syncthreads();
+}
+
+// expm(A) for the Np x Np matrix in buf[1]; buf[0..8] are Np x Np slabs (ld).  Returns pointer to result.
+__device__ double* cta_expm(double** buf, int ld, int np_, double* v0, double* v1, int* m_out, int* s_out,
+                            Smem& sm) {
+  double* A = buf[1]; double* A2 = buf[2]; double* A4 = buf[3]; double* A6 = buf[4];
+  double* B5 = buf[5]; double* B6 = buf[6]; double* B7 = buf[7]; double* B8 = buf[8];
+  cta_gemm(A2, ld, A, ld, A, ld, np_, np_, np_, sm);
+  cta_gemm(A4, ld, A2, ld, A2, ld, np_, np_, np_, sm);
+  cta_gemm(A6, ld, A4, ld, A2, ld, np_, np_, np_, sm);
+  const double normA = cta_norm1(A, ld, np_, sm);
+  const double d4 = pow(cta_norm1(A4, ld, np_, sm), 0.25);
+  const double d6 = pow(cta_norm1(A6, ld, np_, sm), 1.0 / 6.0);
+  const double eta0 = fmax(d4, d6);
+  int m = 0, s = 0;
+  if (eta0 < kTheta[0] && ell_of(cta_absnorm_power(A, ld, np_, 1.0, 7, v0, v1, sm), normA, 0, 3) == 0) m = 3;
+  if (!m && eta0 < kTheta[1] && ell_of(cta_absnorm_power(A, ld, np_, 1.0, 11, v0, v1, sm), normA, 1, 5) == 0) m = 5;
+  double d8 = 0.0, eta2 = 0.0;
+  if (!m) {
+    cta_gemm(B5, ld, A4, ld, A4, ld, np_, np_, np_, sm);   // A^8
+    d8 = pow(cta_norm1(B5, ld, np_, sm), 0.125);
+    eta2 = fmax(d6, d8);
+    if (eta2 < kTheta[2] && ell_of(cta_absnorm_power(A, ld, np_, 1.0, 15, v0, v1, sm), normA, 2, 7) == 0) m = 7;
+    if (!m && eta2 < kTheta[3] && ell_of(cta_absnorm_power(A, ld, np_, 1.0, 19, v0, v1, sm), normA, 3, 9) == 0) m = 9;
+  }
+  double* U = B7; double* V = B8;
+  if (m == 3) {
+    cta_lincomb(B5, ld, np_, kB3[1], A2, kB3[3], nullptr, 0, nullptr, 0, nullptr);
+    cta_gemm(U, ld, A, ld, B5, ld, np_, np_, np_, sm);
+    cta_lincomb(V, ld, np_, kB3[0], A2, kB3[2], nullptr, 0, nullptr, 0, nullptr);
+  } else if (m == 5) {
+    cta_lincomb(B5, ld, np_, kB5[1], A4, kB5[5], A2, kB5[3], nullptr, 0, nullptr);
+    cta_gemm(U, ld, A, ld, B5, ld, np_, np_, np_, sm);
+    cta_lincomb(V, ld, np_, kB5[0], A4, kB5[4], A2, kB5[2], nullptr, 0, nullptr);
+  } else if (m == 7) {
+    cta_lincomb(B5, ld, np_, kB7[1], A6, kB7[7], A4, kB7[5], A2, kB7[3], nullptr);
+    cta_gemm(U, ld, A, ld, B5, ld, np_, np_, np_, sm);
+    cta_lincomb(V, ld, np_, kB7[0], A6, kB7[6], A4, kB7[4], A2, kB7[2], nullptr);
+  } else if (m == 9) {
+    // B5 holds A^8
+    cta_lincomb(B6, ld, np_, kB9[1], A6, kB9[7], A4, kB9[5], A2, kB9[3], nullptr);
+    for (int idx = threadIdx.x; idx < np_ * np_; idx += GT) {
+      const int i = idx / np_, jj = idx - i * np_; const size_t o = (size_t)i * ld + jj;
+      B6[o] += kB9[9] * B5[o];
+    }
+    __syncthreads();
+    cta_gemm(U, ld, A, ld, B6, ld, np_, np_, np_, sm);
+    cta_lincomb(V, ld, np_, kB9[0], A6, kB9[6], A4, kB9[4], A2, kB9[2], nullptr);
+    for (int idx = threadIdx.x; idx < np_ * np_; idx += GT) {
+      const int i = idx / np_, jj = idx - i * np_; const size_t o = (size_t)i * ld + jj;
+      V[o] += kB9[8] * B5[o];
+    }
+    __syncthreads();
+  } else {
+    m = 13;
+    cta_gemm(B6, ld, A4, ld, A6, ld, np_, np_, np_, sm);   // A^10
+    const double d10 = pow(cta_norm1(B6, ld, np_, sm), 0.1);
+    const double eta3 = fmax(d8, d10), eta4 = fmin(eta2, eta3);
+    double sv = ceil(log2(eta4 / kTheta[4]));
+    s = (sv > 0.0) ? (int)sv : 0;
+    if (!(sv == sv) || sv > 2000.0) s = 2000;
+    const double sc = ldexp(1.0, -s);
+    s += ell_of(cta_absnorm_power(A, ld, np_, sc, 27, v0, v1, sm), normA * sc, 4, 13);
+    if (s > 2000) s = 2000;
+    const double s1 = ldexp(1.0, -s), s2 = ldexp(1.0, -2 * s), s4 = ldexp(1.0, -4 * s), s6 = ldexp(1.0, -6 * s);
+    for (int idx = threadIdx.x; idx < np_ * np_; idx += GT) {
+      const int i = idx / np_, jj = idx - i * np_; const size_t o = (size_t)i * ld + jj;
+      A[o] *= s1; A2[o] *= s2; A4[o] *= s4; A6[o] *= s6;
+    }
+    __syncthreads();
+    cta_lincomb(B5, ld, np_, 0.0, A6, kB13[13], A4, kB13[11], A2, kB13[9], nullptr);
+    cta_gemm(B6, ld, A6, ld, B5, ld, np_, np_, np_, sm);                                   // U2
+    cta_lincomb(B5, ld, np_, kB13[1], A6, kB13[7], A4, kB13[5], A2, kB13[3], B6);
+    cta_gemm(U, ld, A, ld, B5, ld, np_, np_, np_, sm);
+    cta_lincomb(B5, ld, np_, 0.0, A6, kB13[12], A4, kB13[10], A2, kB13[8], nullptr);
+    cta_gemm(B6, ld, A6, ld, B5, ld, np_, np_, np_, sm);                                   // V2
+    cta_lincomb(V, ld, np_, kB13[0], A6, kB13[6], A4, kB13[4], A2, kB13[2], B6);
+  }
+  // P = V - U -> B5 ; Q = V + U -> B6 ; solve P X = Q
+  for (int idx = threadIdx.x; idx < np_ * np_; idx += GT) {
+    const int i = idx / np_, jj = idx - i * np_; const size_t o = (size_t)i * ld + jj;
+    const double u = U[o], vv = V[o];
+    B5[o] = vv - u; B6[o] = vv + u;
+  }
+  __syncthreads();
+  cta_lu_solve(B5, B6, ld, np_, sm);
+  double* Xc = B6; double* Xn = B7;
+  for (int it = 0; it < s; ++it) {
+    cta_gemm(Xn, ld, Xc, ld, Xc, ld, np_, np_, np_, sm);
+    double* t = Xc; Xc = Xn; Xn = t;
+  }
+  *m_out = m; *s_out = s;
+  return Xc;
+}
+
+// in-place lower Cholesky of the n x n matrix K (shared, ld LDS); returns 0 or the 1-based failing pivot
+__device__ int cta_cholesky(double* K, int n, Smem& sm) {
+  const int tid = threadIdx.x;
+  for (int k = 0; k < n; ++k) {
+    const double d = K[k * LDS + k];
+    if (!(d > 0.0)) return k + 1;      // uniform: every thread reads the same value
+    const double r = sqrt(d);
+    __syncthreads();
+    if (tid == 0) K[k * LDS + k] = r;
+    for (int i = k + 1 + tid; i < n; i += GT) K[i * LDS + k] /= r;
+    __syncthreads();
+    const int rem = n - k - 1;
+    for (int idx = tid; idx < rem * rem; idx += GT) {
+      const int a = idx / rem, b = idx - a * rem;
+      if (b <= a) {
+        const int i = k + 1 + a, jj = k + 1 + b;
+        K[i * LDS + jj] = fma(-K[i * LDS + k], K[jj * LDS + k], K[i * LDS + jj]);
+      }
+    }
+    __syncthreads();
+  }
+  return 0;
+}
+// warp 0: forward substitution tmp = L^-1 b (row dot products split over the 32 lanes)
+__device__ __forceinline__ void warp_fwd_solve(const double* L, int n, const double* b, double* tmp, int lane) {
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int c = lane; c < i; c += 32) s = fma(L[i * LDS + c], tmp[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) tmp[i] = (b[i] - s) / L[i * LDS + i];
+    __syncwarp();
+  }
+}
+// warp 0: backward substitution x = L^-T tmp
+__device__ __forceinline__ void warp_bwd_solve(const double* L, int n, const double* tmp, double* x, int lane) {
+  for (int i = n - 1; i >= 0; --i) {
+    double s = 0.0;
+    for (int c = i + 1 + lane; c < n; c += 32) s = fma(L[c * LDS + i], x[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) x[i] = (tmp[i] - s) / L[i * LDS + i];
+    __syncwarp();
+  }
+}
+// x = L^-T L^-1 b
+__device__ void cta_chol_solve(const double* L, int n, const double* b, double* x, double* tmp) {
+  if (threadIdx.x < 32) {
+    warp_fwd_solve(L, n, b, tmp, threadIdx.x);
+    warp_bwd_solve(L, n, tmp, x, threadIdx.x);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(GT, 1)
+k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __restrict__ y_all,
+              const double* __restrict__ anom_sic, const int32_t* __restrict__ n_areas_sic, int ma_sic, int ts_sic,
+              const double* __restrict__ anom_sst, const int32_t* __restrict__ n_areas_sst, int ma_sst, int ts_sst,
+              int max_pred, SieGpResult* __restrict__ out, unsigned char* __restrict__ scratch, size_t per_cta) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smraw);
+  const int tid = threadIdx.x;
+  const int ld = max_pred;
+  unsigned char* sp = scratch + (size_t)blockIdx.x * per_cta;
+  double* buf[9];
+  for (int i = 0; i < 9; ++i) buf[i] = reinterpret_cast<double*>(sp) + (size_t)i * ld * ld;
+  double* Xg = reinterpret_cast<double*>(sp) + (size_t)9 * ld * ld;   // (n+1) x Np, ld
+  double* XE = Xg + (size_t)MAXN * ld;                                 // n x Np
+  double* XM = XE + (size_t)MAXN * ld;                                 // n x Np (gradient)
+  double* v0 = XM + (size_t)MAXN * ld;
+  double* v1 = v0 + ld;
+  double* colm = v1 + ld;                                              // column means / scratch [ld]
+  double* Gg = colm + ld;                                              // [MAXN*LDS] gradient scratch
+  int* sel = reinterpret_cast<int*>(Gg + MAXN * LDS);                  // [ld] selected series (sign in bit 30)
+
+  for (int p = blockIdx.x; p < P; p += gridDim.x) {
+    const SieGpProblem pr = prob[p];
+    const int n = pr.n;
+    SieGpResult res;
+    res.fmean = res.fvar = res.sigma_f = res.nlml = res.g_ell = res.g_sig = sie_nan();
+    res.n_pred = 0; res.expm_m = 0; res.expm_s = 0; res.info = 0;
+    __syncthreads();
+    if (n < 2 || n + 1 > MAXN) {
+      if (tid == 0) { res.info = -2; out[p] = res; }
+      continue;
+    }
+    const int na1 = n_areas_sic[pr.job_sic];
+    const int na2 = (pr.job_sst >= 0) ? n_areas_sst[pr.job_sst] : 0;
+    const double* s1 = anom_sic + (size_t)pr.job_sic * ma_sic * ts_sic;
+    const double* s2 = (pr.job_sst >= 0) ? anom_sst + (size_t)pr.job_sst * ma_sst * ts_sst : nullptr;
+    // ---- y, centred/normalised copy for pearsonr (scipy: xm/||xm|| . ym/||ym||)
+    for (int t = tid; t < n; t += GT) sm.y[t] = y_all[pr.y_off + t];
+    __syncthreads();
+    double ymean = 0.0;
+    for (int t = 0; t < n; ++t) ymean += sm.y[t];
+    ymean /= (double)n;
+    double ynorm = 0.0;
+    for (int t = 0; t < n; ++t) { const double d = sm.y[t] - ymean; ynorm = fma(d, d, ynorm); }
+    ynorm = sqrt(ynorm);
+    // ---- predictor selection (north/June1st.py:216-224)
+    if (tid == 0) sm.misc[0] = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < na1 + na2; c0 += GT) {
+      const int c = c0 + tid;
+      int flag = 0;   // 0 no, 1 take, 2 take negated
+      if (c < na1 + na2) {
+        const bool sst = c >= na1;
+        const double* x = sst ? s2 + (size_t)(c - na1) * ts_sst : s1 + (size_t)c * ts_sic;
+        double xm = 0.0;
+        for (int t = 0; t < n; ++t) xm += x[t];
+        xm /= (double)n;
+        double xn = 0.0, dot = 0.0;
+        for (int t = 0; t < n; ++t) { const double d = x[t] - xm; xn = fma(d, d, xn); dot = fma(d, sm.y[t] - ymean, dot); }
+        double r = dot / (sqrt(xn) * ynorm);
+        r = fmax(-1.0, fmin(1.0, r));
+        if (sst) flag = (r < 0.0) ? 2 : 0;
+        else if (pr.rule == 1) flag = 1;
+        else if (pr.rule == 0) flag = (r > 0.0) ? 1 : 0;
+        else flag = (r > 0.0 && r > pr.r_sel) ? 1 : 0;
+      }
+      // order-preserving compaction across the CTA
+      const unsigned bal = __ballot_sync(0xffffffffu, flag != 0);
+      const int lane = tid & 31, w = tid >> 5;
+      if (lane == 0) sm.ired[w] = __popc(bal);
+      __syncthreads();
+      int off = sm.misc[0];
+      for (int i = 0; i < w; ++i) off += sm.ired[i];
+      if (flag) {
+        const int pos = off + __popc(bal & ((1u << lane) - 1u));
+        if (pos < ld) sel[pos] = c | (flag == 2 ? (1 << 30) : 0);
+      }
+      __syncthreads();
+      if (tid == 0) { int tot = 0; for (int i = 0; i < GT / 32; ++i) tot += sm.ired[i]; sm.misc[0] += tot; }
+      __syncthreads();
+    }
+    const int np_ = sm.misc[0];
+    res.n_pred = np_;
+    if (np_ == 0 || np_ > ld) {
+      if (tid == 0) { res.info = (np_ == 0) ? -1 : -2; out[p] = res; }
+      continue;
+    }
+    // ---- X (n+1 rows) with optional column z-score over all n+1 rows (:226-227)
+    for (int c = tid; c < np_; c += GT) {
+      const int sc = sel[c] & ~(1 << 30);
+      const double sign = (sel[c] & (1 << 30)) ? -1.0 : 1.0;
+      const double* x = (sc >= na1) ? s2 + (size_t)(sc - na1) * ts_sst : s1 + (size_t)sc * ts_sic;
+      if (pr.zscore) {
+        double mu = 0.0;
+        for (int t = 0; t <= n; ++t) mu += sign * x[t];
+        mu /= (double)(n + 1);
+        double var = 0.0;
+        for (int t = 0; t <= n; ++t) { const double d = sign * x[t] - mu; var = fma(d, d, var); }
+        const double sd = sqrt(var / (double)(n + 1));
+        for (int t = 0; t <= n; ++t) Xg[(size_t)t * ld + c] = (sign * x[t] - mu) / sd;
+      } else {
+        for (int t = 0; t <= n; ++t) Xg[(size_t)t * ld + c] = sign * x[t];
+      }
+      double cm = 0.0;                       // column mean over the n training rows for the covariance
+      for (int t = 0; t < n; ++t) cm += Xg[(size_t)t * ld + c];
+      colm[c] = cm / (double)n;
+    }
+    __syncthreads();
+    // ---- M = |cov(X, bias=True)|, zero diagonal, diagonal = -column sums (:231-233) -> buf[0]
+    double* M = buf[0];
+    const double invn = 1.0 / (double)n;
+    for (int idx = tid; idx < np_ * np_; idx += GT) {
+      const int i = idx / np_, jj = idx - i * np_;
+      double sacc = 0.0;
+      if (i != jj) {
+        const double mi = colm[i], mj = colm[jj];
+        for (int t = 0; t < n; ++t) sacc = fma(Xg[(size_t)t * ld + i] - mi, Xg[(size_t)t * ld + jj] - mj, sacc);
+        sacc = fabs(sacc * invn);
+      }
+      M[(size_t)i * ld + jj] = sacc;
+    }
+    __syncthreads();
+    for (int jj = tid; jj < np_; jj += GT) {
+      double sacc = 0.0;
+      for (int i = 0; i < np_; ++i) sacc += M[(size_t)i * ld + jj];
+      colm[jj] = sacc;
+    }
+    __syncthreads();
+    for (int jj = tid; jj < np_; jj += GT) M[(size_t)jj * ld + jj] = -colm[jj];
+    __syncthreads();
+    // ---- Sigma~ = expm(l*M)
+    for (int idx = tid; idx < np_ * np_; idx += GT) {
+      const int i = idx / np_, jj = idx - i * np_;
+      buf[1][(size_t)i * ld + jj] = pr.ell * M[(size_t)i * ld + jj];
+    }
+    __syncthreads();
+    int em = 0, es = 0;
+    const double* E = cta_expm(buf, ld, np_, v0, v1, &em, &es, sm);
+    res.expm_m = em; res.expm_s = es;
+    // ---- W = X Sigma~ X^T : XE = X E (n x Np), then W = XE X^T (n x n, shared)
+    cta_gemm(XE, ld, Xg, ld, E, ld, n, np_, np_, sm);
+    for (int idx = tid; idx < n * n; idx += GT) {
+      const int i = idx / n, jj = idx - i * n;
+      double sacc = 0.0;
+      for (int c = 0; c < np_; ++c) sacc = fma(XE[(size_t)i * ld + c], Xg[(size_t)jj * ld + c], sacc);
+      sm.W[i * LDS + jj] = sacc;
+    }
+    __syncthreads();
+    // ---- L~ = chol(W + sig I); A~ ; sigma_f = y^T A~ / n  (:265-267)
+    for (int idx = tid; idx < n * n; idx += GT) {
+      const int i = idx / n, jj = idx - i * n;
+      sm.K[i * LDS + jj] = sm.W[i * LDS + jj] + ((i == jj) ? pr.sig : 0.0);
+    }
+    __syncthreads();
+    int info = cta_cholesky(sm.K, n, sm);
+    if (info) { if (tid == 0) { res.info = info; out[p] = res; } continue; }
+    cta_chol_solve(sm.K, n, sm.y, sm.ya, sm.v);
+    double sf = 0.0;
+    for (int t = 0; t < n; ++t) sf = fma(sm.y[t], sm.ya[t], sf);
+    sf /= (double)n;
+    const double sn = sf * pr.sig;
+    res.sigma_f = sf;
+    __syncthreads();
+    // ---- L = chol(sf*W + sn I); alpha (:269-271)
+    for (int idx = tid; idx < n * n; idx += GT) {
+      const int i = idx / n, jj = idx - i * n;
+      sm.K[i * LDS + jj] = sf * sm.W[i * LDS + jj] + ((i == jj) ? sn : 0.0);
+    }
+    __syncthreads();
+    info = cta_cholesky(sm.K, n, sm);
+    if (info) { if (tid == 0) { res.info = info; out[p] = res; } continue; }
+    cta_chol_solve(sm.K, n, sm.y, sm.alpha, sm.v);
+    // ---- predictive mean / variance (:272-277)
+    for (int i = tid; i < n; i += GT) {
+      double sacc = 0.0;
+      for (int c = 0; c < np_; ++c) sacc = fma(XE[(size_t)i * ld + c], Xg[(size_t)n * ld + c], sacc);
+      sm.kxs[i] = sf * sacc;
+    }
+    __syncthreads();
+    // KXsXs = xs Sigma xs^T + sn : thread per column of E, then a block sum
+    double kss_part = 0.0;
+    for (int c = tid; c < np_; c += GT) {
+      double row = 0.0;
+      for (int d = 0; d < np_; ++d) row = fma(Xg[(size_t)n * ld + d], E[(size_t)d * ld + c], row);
+      kss_part = fma(row, Xg[(size_t)n * ld + c], kss_part);
+    }
+    const double kss = sf * block_sum(kss_part, sm) + sn;
+    if (tid < 32) {
+      warp_fwd_solve(sm.K, n, sm.kxs, sm.v, tid);          // v = L^-1 KXXs
+      double vv = 0.0, fm = 0.0, ya = 0.0, ld_sum = 0.0;
+      for (int i = tid; i < n; i += 32) {
+        vv = fma(sm.v[i], sm.v[i], vv);
+        fm = fma(sm.kxs[i], sm.alpha[i], fm);
+        ya = fma(sm.y[i], sm.alpha[i], ya);
+        ld_sum += log(sm.K[i * LDS + i]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        vv += __shfl_xor_sync(0xffffffffu, vv, o);
+        fm += __shfl_xor_sync(0xffffffffu, fm, o);
+        ya += __shfl_xor_sync(0xffffffffu, ya, o);
+        ld_sum += __shfl_xor_sync(0xffffffffu, ld_sum, o);
+      }
+      if (tid == 0) {
+        sm.dmisc[0] = fm; sm.dmisc[1] = kss - vv;
+        sm.dmisc[2] = ya / 2 + ld_sum + n * log(2 * 3.141592653589793238462643383279502884) / 2;
+      }
+    }
+    __syncthreads();
+    res.fmean = sm.dmisc[0]; res.fvar = sm.dmisc[1]; res.nlml = sm.dmisc[2];
+    // ---- MLII gradient as written at :248-252
+    if (pr.want_grad) {
+      // dKdl = X (M Sigma) X^T + sn I, Sigma = sf * E
+      double* MS = buf[5];
+      cta_gemm(MS, ld, M, ld, E, ld, np_, np_, np_, sm);
+      cta_gemm(XM, ld, Xg, ld, MS, ld, n, np_, np_, sm);
+      for (int which = 0; which < 2; ++which) {
+        for (int idx = tid; idx < n * n; idx += GT) {
+          const int i = idx / n, jj = idx - i * n;
+          double val;
+          if (which == 0) {
+            double sacc = 0.0;
+            for (int c = 0; c < np_; ++c) sacc = fma(XM[(size_t)i * ld + c], Xg[(size_t)jj * ld + c], sacc);
+            val = sf * sacc + ((i == jj) ? sn : 0.0);
+          } else {
+            val = sf * sm.W[i * LDS + jj] + ((i == jj) ? sf : 0.0);
+          }
+          Gg[i * LDS + jj] = val;
+        }
+        __syncthreads();
+        // quad = alpha^T dK alpha ; trace(K^-1 dK) by solving column by column (thread per column)
+        double quad = 0.0;
+        for (int idx = tid; idx < n * n; idx += GT) {
+          const int i = idx / n, jj = idx - i * n;
+          quad = fma(sm.alpha[i] * Gg[i * LDS + jj], sm.alpha[jj], quad);
+        }
+        quad = block_sum(quad, sm);
+        double tr = 0.0;
+        if (tid < n) {
+          double col[MAXN];
+          const int jj = tid;
+          for (int i = 0; i < n; ++i) {
+            double sacc = Gg[i * LDS + jj];
+            for (int c = 0; c < i; ++c) sacc = fma(-sm.K[i * LDS + c], col[c], sacc);
+            col[i] = sacc / sm.K[i * LDS + i];
+          }
+          for (int i = n - 1; i >= jj; --i) {
+            double sacc = col[i];
+            for (int c = i + 1; c < n; ++c) sacc = fma(-sm.K[c * LDS + i], col[c], sacc);
+            col[i] = sacc / sm.K[i * LDS + i];
+          }
+          tr = col[jj];
+        }
+        tr = block_sum(tr, sm);
+        const double gval = tr / 2 - quad / 2;
+        if (which == 0) res.g_ell = gval; else res.g_sig = gval;
+        __syncthreads();
+      }
+    }
+    if (tid == 0) out[p] = res;
+  }
+}
+
+__host__ size_t gp_per_cta_bytes(int max_pred) {
+  size_t d = (size_t)9 * max_pred * max_pred + (size_t)3 * MAXN * max_pred + (size_t)3 * max_pred + (size_t)MAXN * LDS;
+  size_t bytes = d * sizeof(double) + (size_t)max_pred * sizeof(int);
+  return (bytes + 255) / 256 * 256;
+}
+int gp_grid(int P) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+  } else {
+    (void)cudaGetLastError();
+  }
+  const int g = 2 * sms;     // shared memory (~86 KB) allows two CTAs per SM
+  return P < g ? P : g;
+}
+
+}  // namespace
+
+extern "C" size_t sie_gp_scratch_bytes(int P, int max_pred, int max_n) {
+  (void)max_n;
+  return (size_t)gp_grid(P > 0 ? P : 1) * gp_per_cta_bytes(max_pred);
+}
+
+extern "C" int sie_gp_forecast(const SieGpProblem* prob, int P, const double* y_all, const double* anom_sic,
+                               const int32_t* n_areas_sic, int max_areas_sic, int Tstride_sic,
+                               const double* anom_sst, const int32_t* n_areas_sst, int max_areas_sst,
+                               int Tstride_sst, int max_pred, SieGpResult* out, void* scratch,
+                               size_t scratch_bytes, void* stream) {
+  SIE_CHECK_ARG(prob && y_all && anom_sic && n_areas_sic && out && scratch, "null pointer");
+  SIE_CHECK_ARG(P > 0 && max_pred > 0 && (max_pred % 4) == 0, "P>0 and max_pred a positive multiple of 4");
+  const size_t per = gp_per_cta_bytes(max_pred);
+  int grid = gp_grid(P);
+  if ((size_t)grid * per > scratch_bytes) grid = (int)(scratch_bytes / per);
+  SIE_CHECK_ARG(grid >= 1, "scratch too small");
+  const size_t smem = sizeof(Smem);
+  cudaFuncSetAttribute(k_gp_forecast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_gp_forecast<<<grid, GT, smem, (cudaStream_t)stream>>>(prob, P, y_all, anom_sic, n_areas_sic, max_areas_sic,
+                                                         Tstride_sic, anom_sst, n_areas_sst, max_areas_sst,
+                                                         Tstride_sst, max_pred, out, (unsigned char*)scratch, per);
+  SIE_CHECK_LAUNCH();
+  return SIE_OK;
+}

@@ -1,0 +1,187 @@
+"""Device-resident batch engine: B network builds of one grid shape through K1..K6 of libsie_b200.
+
+PyTorch is used for device memory, pinned host staging and streams only; every number is produced by the
+CUDA kernels behind the C ABI (include/sie_b200.h).  There is no CPU implementation to fall back to.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.SieError("seaiceextentforecasting_b200 needs a CUDA device (sm_100a); there is no CPU path")
+
+
+@functools.lru_cache(maxsize=None)
+def r_crit_ttest(T, alpha):
+    """Critical correlation for the one-sided t-test of ComplexNetworks.py:41-45:
+    P = t.sf(R*sqrt(df/(1-R^2)), df) < alpha  <=>  R > t_c/sqrt(df+t_c^2), t_c = t.isf(alpha, df), df = T-2."""
+    from scipy import stats
+    df = T - 2
+    if df <= 0:
+        return float("nan")
+    tc = stats.t.isf(alpha, df)
+    return float(tc / np.sqrt(df + tc * tc))
+
+
+@functools.lru_cache(maxsize=None)
+def r_crit_pearson(n, alpha):
+    """Critical r of scipy.stats.pearsonr's p-value: (r>0)&(p/2<alpha) <=> r > beta(n/2-1,n/2-1,-1,2).isf(alpha)
+    (north/August1st.py:178-181)."""
+    from scipy import stats
+    if n <= 2:
+        return float("nan")
+    return float(stats.beta(n / 2.0 - 1.0, n / 2.0 - 1.0, loc=-1.0, scale=2.0).isf(alpha))
+
+
+def pad_T(T):
+    """Row length of z: the smallest Tp >= T with Tp = 4 (mod 8): k-steps of 4 for DMMA.8x8x4 and a row stride
+    whose 64-bit fragment loads fall in distinct shared-memory banks."""
+    Tp = max(4, (T + 3) // 4 * 4)
+    while Tp % 8 != 4:
+        Tp += 4
+    return Tp
+
+
+def h2d(arr, dtype=None):
+    """numpy -> pinned staging -> device (async on the current stream)."""
+    a = np.ascontiguousarray(arr, dtype=dtype)
+    t = torch.from_numpy(a)
+    try:
+        t = t.pin_memory()
+    except RuntimeError:
+        pass
+    return t.to("cuda", non_blocking=True)
+
+
+class NetworkBatch:
+    """B jobs (network builds) on one (X, Y) grid.  All buffers are allocated once and reused."""
+
+    def __init__(self, X, Y, Tstride, B, latlon, n_upper=None, max_areas=None, keep_R=True):
+        require_cuda()
+        self.lib = _lib.load()
+        self.X, self.Y, self.C = int(X), int(Y), int(X) * int(Y)
+        self.Tstride, self.B, self.latlon = int(Tstride), int(B), bool(latlon)
+        self.Tp = pad_T(self.Tstride)
+        n_upper = self.C if n_upper is None else int(n_upper)
+        self.ldn = max(128, (n_upper + 127) // 128 * 128)
+        self.MA = int(max_areas) if max_areas else min(self.C // 2 + 1, 1024)
+        dev = "cuda"
+        f64, i32 = torch.float64, torch.int32
+        B_, C_, ldn, MA, Ts, Tp = self.B, self.C, self.ldn, self.MA, self.Tstride, self.Tp
+        self.dt = torch.empty((B_, C_, Ts), dtype=f64, device=dev)
+        self.trend = torch.empty((B_, C_, 2), dtype=f64, device=dev)
+        self.z = torch.empty((B_, ldn, Tp), dtype=f64, device=dev)
+        self.node_cell = torch.empty((B_, ldn), dtype=i32, device=dev)
+        self.cell_node = torch.empty((B_, C_), dtype=i32, device=dev)
+        self.n_nodes = torch.empty((B_,), dtype=i32, device=dev)
+        self.first_nan = torch.empty((B_,), dtype=i32, device=dev)
+        self.status = torch.zeros((B_,), dtype=i32, device=dev)
+        self.R = torch.empty((B_, ldn, ldn), dtype=f64, device=dev) if keep_R else None
+        self.tau_scratch_bytes = int(self.lib.sie_corr_tau_scratch_bytes(B_, ldn))
+        self.tau_scratch = torch.empty((self.tau_scratch_bytes + 7) // 8, dtype=f64, device=dev)
+        self.tau_sum = torch.empty((B_,), dtype=f64, device=dev)
+        self.tau_cnt = torch.empty((B_,), dtype=torch.int64, device=dev)
+        self.tau = torch.empty((B_,), dtype=f64, device=dev)
+        self.stencil = torch.empty((B_, ldn, 4), dtype=f64, device=dev)
+        self.area_cells = torch.empty((B_, C_), dtype=i32, device=dev)
+        self.area_start = torch.empty((B_, MA + 1), dtype=i32, device=dev)
+        self.area_key = torch.empty((B_, MA), dtype=i32, device=dev)
+        self.n_areas = torch.zeros((B_,), dtype=i32, device=dev)
+        self.label = torch.empty((B_, C_), dtype=i32, device=dev)
+        self.area_scratch_bytes = int(self.lib.sie_area_level_scratch_bytes(B_, C_))
+        self.area_scratch = torch.empty((self.area_scratch_bytes + 7) // 8, dtype=f64, device=dev)
+        self.anomaly = torch.zeros((B_, MA, Ts), dtype=f64, device=dev)
+        self.links = torch.zeros((B_, MA, MA), dtype=f64, device=dev)
+        self.strength = torch.zeros((B_, MA), dtype=f64, device=dev)
+        self.strengthmap = torch.empty((B_, C_), dtype=f64, device=dev)
+        self.job_T = None
+        self.launches = 0
+
+    # ---- stages -------------------------------------------------------------------------------
+    def detrend_zscore(self, fields, job_field, job_T, do_detrend=True):
+        """K1.  fields: device [F, C, Tstride]; job_field/job_T: device int32 [B]."""
+        self.job_T = job_T
+        dt = self.dt if do_detrend else fields
+        if not do_detrend:
+            assert fields.shape[0] == self.B, "pass-through mode needs one field per job"
+            self.dt = fields
+        rc = self.lib.sie_detrend_zscore(_ptr(fields), _ptr(job_field), _ptr(job_T), self.B, self.C, self.Tstride,
+                                         self.Tp, 1 if do_detrend else 0, _ptr(dt), _ptr(self.trend), _ptr(self.z),
+                                         _ptr(self.node_cell), _ptr(self.cell_node), _ptr(self.n_nodes),
+                                         _ptr(self.first_nan), _ptr(self.status), self.ldn, _stream())
+        _lib.check(rc, "sie_detrend_zscore")
+        self.launches += 3
+
+    def corr_tau(self, r_crit, store_R=True, shard_rank=0, shard_count=1):
+        """K2.  r_crit: device float64 [B]."""
+        R = self.R if store_R else None
+        rc = self.lib.sie_corr_tau(_ptr(self.z), _ptr(self.n_nodes), _ptr(self.job_T), _ptr(r_crit), self.B,
+                                   self.ldn, self.Tp, _ptr(R), _ptr(self.tau_scratch), self.tau_scratch_bytes,
+                                   _ptr(self.tau_sum), _ptr(self.tau_cnt), _ptr(self.tau), shard_rank, shard_count,
+                                   _stream())
+        _lib.check(rc, "sie_corr_tau")
+        self.launches += 3
+
+    def area_level(self):
+        """K3 + K4/K5."""
+        rc = self.lib.sie_corr_stencil(_ptr(self.R), _ptr(self.node_cell), _ptr(self.cell_node), _ptr(self.n_nodes),
+                                       self.B, self.X, self.Y, self.ldn, int(self.latlon), _ptr(self.stencil),
+                                       _stream())
+        _lib.check(rc, "sie_corr_stencil")
+        rc = self.lib.sie_area_level(_ptr(self.R), _ptr(self.stencil), _ptr(self.node_cell), _ptr(self.cell_node),
+                                     _ptr(self.n_nodes), _ptr(self.tau), _ptr(self.first_nan), self.B, self.X,
+                                     self.Y, self.ldn, int(self.latlon), self.MA, _ptr(self.area_cells),
+                                     _ptr(self.area_start), _ptr(self.area_key), _ptr(self.n_areas),
+                                     _ptr(self.label), _ptr(self.status), _ptr(self.area_scratch),
+                                     self.area_scratch_bytes, _stream())
+        _lib.check(rc, "sie_area_level")
+        self.launches += 2
+
+    def intra_links(self, scale):
+        """K6.  scale: device float64 [C] (already square-rooted weights)."""
+        rc = self.lib.sie_intra_links(_ptr(self.dt), _ptr(scale), _ptr(self.job_T), _ptr(self.area_cells),
+                                      _ptr(self.area_start), _ptr(self.n_areas), _ptr(self.label), self.B, self.C,
+                                      self.Tstride, self.MA, _ptr(self.anomaly), _ptr(self.links),
+                                      _ptr(self.strength), _ptr(self.strengthmap), _stream())
+        _lib.check(rc, "sie_intra_links")
+        self.launches += 3
+
+    def build(self, fields, job_field, job_T, r_crit, scale, do_detrend=True):
+        self.detrend_zscore(fields, job_field, job_T, do_detrend)
+        self.corr_tau(r_crit)
+        self.area_level()
+        self.intra_links(scale)
+
+    # ---- host views ---------------------------------------------------------------------------
+    def areas_to_host(self):
+        """-> per job: (status, [(key, [[i,j],...]), ...]) in the reference's dict order."""
+        n_areas = self.n_areas.cpu().numpy()
+        status = self.status.cpu().numpy()
+        starts = self.area_start.cpu().numpy()
+        keys = self.area_key.cpu().numpy()
+        cells = self.area_cells.cpu().numpy()
+        out = []
+        Y = self.Y
+        for b in range(self.B):
+            V = {}
+            for a in range(int(n_areas[b])):
+                seg = cells[b, starts[b, a]:starts[b, a + 1]]
+                V[int(keys[b, a])] = [[int(c // Y), int(c % Y)] for c in seg]
+            out.append((int(status[b]), V))
+        return out

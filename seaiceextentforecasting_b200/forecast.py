@@ -1,0 +1,329 @@
+"""Host-side mirror of the script-level helpers every reference script re-defines -- `detrend`, `networks`,
+`forecast` (+ nested `MLII`), `skill` -- with explicit arguments instead of module globals, plus the batched
+retrospective sweep that is the headline workload (north/retrospective_forecasts/*_retro.py: years
+fmin..fmax x init months x 3 regions).  All arithmetic runs in libsie_b200's kernels.
+
+Reference lines: detrend north/June1st.py:179-194 (retro: June1st_retro.py:178-195); networks :196-206;
+forecast :208-288; MLII :235-257; read_SIE de-trending June1st_retro.py:58-69; skill :293-314.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import CONFIGS, RULE_POS_SIG, ForecastConfig
+from .engine import NetworkBatch, _ptr, _stream, h2d, r_crit_pearson, r_crit_ttest, require_cuda
+
+FIRST_YEAR = 1979
+
+GP_PROBLEM_DTYPE = np.dtype([("job_sic", "<i4"), ("job_sst", "<i4"), ("n", "<i4"), ("y_off", "<i4"),
+                             ("rule", "<i4"), ("zscore", "<i4"), ("want_grad", "<i4"), ("pad_", "<i4"),
+                             ("r_sel", "<f8"), ("ell", "<f8"), ("sig", "<f8")])
+GP_RESULT_DTYPE = np.dtype([("fmean", "<f8"), ("fvar", "<f8"), ("sigma_f", "<f8"), ("nlml", "<f8"),
+                            ("g_ell", "<f8"), ("g_sig", "<f8"), ("n_pred", "<i4"), ("expm_m", "<i4"),
+                            ("expm_s", "<i4"), ("info", "<i4")])
+assert GP_PROBLEM_DTYPE.itemsize == C.sizeof(_lib.SieGpProblem)
+assert GP_RESULT_DTYPE.itemsize == C.sizeof(_lib.SieGpResult)
+
+
+# ------------------------------------------------------------------------------------------------
+# single-call helpers (reference call surface)
+# ------------------------------------------------------------------------------------------------
+def detrend(data):
+    """`detrend(dataset)` (north/June1st.py:179-194): (X,Y,T) -> (dt (X,Y,T), trend (X,Y,2))."""
+    require_cuda()
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    X, Y, T = data.shape
+    n_upper = int((~np.isnan(data).any(axis=2)).sum())
+    eng = NetworkBatch(X, Y, T, 1, latlon=False, n_upper=n_upper, keep_R=False, max_areas=1)
+    fields = h2d(data.reshape(1, X * Y, T))
+    jf = torch.zeros(1, dtype=torch.int32, device="cuda")
+    jT = torch.full((1,), T, dtype=torch.int32, device="cuda")
+    eng.detrend_zscore(fields, jf, jT, do_detrend=True)
+    return (eng.dt[0].cpu().numpy().reshape(X, Y, T), eng.trend[0].cpu().numpy().reshape(X, Y, 2))
+
+
+def networks(dt, area=None, lat=None, latlon=True, significance=0.01):
+    """`networks(dataset, latlon)` (north/June1st.py:196-206) -> (nodes = V, anoms = anomaly)."""
+    from .ComplexNetworks import Network
+    net = Network(data=dt)
+    Network.tau(net, significance)
+    Network.area_level(net, latlon_grid=latlon)
+    if latlon:
+        Network.intra_links(net, lat=lat)
+    else:
+        Network.intra_links(net, area=area)
+    return net.V, net.anomaly
+
+
+def sie_detrend_tables(sie, fmin, fmax):
+    """The de-trending arithmetic of `read_SIE` (north/retrospective_forecasts/June1st_retro.py:58-69): one OLS
+    fit per end-year on the prefix window; `dt` rounded to 3 d.p., `trend` = [slope, intercept] un-rounded.
+    O(years^2) scalar work on the host (not a kernel)."""
+    rows = fmax - (fmin - 1) + 1
+    trend = np.zeros((rows, 2))
+    dt = np.zeros((rows, fmax - FIRST_YEAR + 1))
+    sie = np.asarray(sie, dtype=np.float64)
+    for year in range(fmin - 1, fmax + 1):
+        n = year - FIRST_YEAR + 1
+        x = np.arange(n, dtype=np.float64)
+        y = sie[:n]
+        xm, ym = x.mean(), y.mean()
+        slope = np.mean((x - xm) * (y - ym)) / np.mean((x - xm) ** 2)
+        icpt = ym - slope * xm
+        trend[year - (fmin - 1)] = (slope, icpt)
+        dt[year - (fmin - 1), :n] = y - (slope * x + icpt)
+    return dt.round(3), trend
+
+
+def skill(obs_rt, forecast_rt, obs_dt, forecast_dt):
+    """`skill()` (north/retrospective_forecasts/June1st_retro.py:293-314): 1 - MSE/MSE_clim, 3 d.p."""
+    a = np.mean((obs_rt - forecast_rt) ** 2)
+    b = np.mean((obs_rt - np.nanmean(obs_rt)) ** 2)
+    c = np.mean((obs_dt - forecast_dt) ** 2)
+    d = np.mean((obs_dt - np.nanmean(obs_dt)) ** 2)
+    return (1 - (a / b)).round(3), (1 - (c / d)).round(3)
+
+
+# ------------------------------------------------------------------------------------------------
+# batched GP
+# ------------------------------------------------------------------------------------------------
+class GpBatch:
+    """P GP problems over one or two anomaly sets held by NetworkBatch objects."""
+
+    def __init__(self, P, max_pred=256):
+        require_cuda()
+        self.lib = _lib.load()
+        self.P = int(P)
+        self.max_pred = int((max_pred + 3) // 4 * 4)
+        self.scratch_bytes = int(self.lib.sie_gp_scratch_bytes(self.P, self.max_pred, 64))
+        self.scratch = torch.empty((self.scratch_bytes + 7) // 8, dtype=torch.float64, device="cuda")
+        self.out = torch.empty(self.P * GP_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+
+    def run(self, prob_dev, y_dev, sic: NetworkBatch, sst: NetworkBatch | None):
+        rc = self.lib.sie_gp_forecast(
+            _ptr(prob_dev), self.P, _ptr(y_dev), _ptr(sic.anomaly), _ptr(sic.n_areas), sic.MA, sic.Tstride,
+            _ptr(sst.anomaly) if sst is not None else C.c_void_p(0),
+            _ptr(sst.n_areas) if sst is not None else C.c_void_p(0),
+            sst.MA if sst is not None else 0, sst.Tstride if sst is not None else 0,
+            self.max_pred, _ptr(self.out), _ptr(self.scratch), self.scratch_bytes, _stream())
+        _lib.check(rc, "sie_gp_forecast")
+
+    def results(self):
+        return self.out.cpu().numpy().view(GP_RESULT_DTYPE)
+
+
+def forecast(y, anoms_sic, anoms_sst=None, rule=0, alpha=0.05, zscore=False, ell=1.0, sig=1.0, want_grad=False):
+    """One GP forecast from node series given as dicts (the reference's `dataset['anoms']`), i.e. the body of
+    `forecast()` for one region (north/June1st.py:214-277).  Returns the raw result record."""
+    require_cuda()
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    n = y.size
+
+    def pack(anoms):
+        keys = list(anoms)
+        arr = np.zeros((1, max(1, len(keys)), n + 1))
+        for a, k in enumerate(keys):
+            arr[0, a] = np.asarray(anoms[k], dtype=np.float64)[:n + 1]
+        return arr, len(keys)
+
+    class _Set:   # minimal stand-in exposing what GpBatch.run reads
+        pass
+
+    sets = []
+    for anoms in (anoms_sic, anoms_sst):
+        if anoms is None:
+            sets.append(None)
+            continue
+        arr, na = pack(anoms)
+        s = _Set()
+        s.anomaly = h2d(arr)
+        s.n_areas = torch.tensor([na], dtype=torch.int32, device="cuda")
+        s.MA = arr.shape[1]
+        s.Tstride = n + 1
+        sets.append(s)
+    prob = np.zeros(1, dtype=GP_PROBLEM_DTYPE)
+    prob["job_sic"] = 0
+    prob["job_sst"] = 0 if anoms_sst is not None else -1
+    prob["n"] = n
+    prob["rule"] = rule
+    prob["zscore"] = int(zscore)
+    prob["want_grad"] = int(want_grad)
+    prob["r_sel"] = r_crit_pearson(n, alpha) if rule == RULE_POS_SIG else 0.0
+    prob["ell"] = ell
+    prob["sig"] = sig
+    npred = sets[0].MA + (sets[1].MA if sets[1] is not None else 0)
+    gp = GpBatch(1, max_pred=max(4, npred))
+    gp.run(h2d(prob.view(np.uint8)), h2d(y), sets[0], sets[1])
+    return gp.results()[0]
+
+
+def mlii(theta, y, anoms_sic, anoms_sst=None, rule=0, alpha=0.05, zscore=False):
+    """`MLII(hyperparameters)` (north/June1st.py:235-257): theta = (log l, log sigma_n~) ->
+    (nlML, [d/dtheta1, d/dtheta2]); (inf, [inf, inf]) when the kernel matrix is not SPD."""
+    r = forecast(y, anoms_sic, anoms_sst, rule, alpha, zscore, float(np.exp(theta[0])), float(np.exp(theta[1])),
+                 want_grad=True)
+    if r["info"] != 0:
+        return np.inf, np.asarray([np.inf, np.inf])
+    return np.float64(r["nlml"]), np.asarray([r["g_ell"], r["g_sig"]])
+
+
+# ------------------------------------------------------------------------------------------------
+# retrospective sweep
+# ------------------------------------------------------------------------------------------------
+class RetrospectiveSweep:
+    """years fmin..fmax x the given init-month configs x 3 regions, in one device-resident batch.
+
+    sic_fields : dict config-name -> (X, Y, Tfull) raw monthly SIC of that init's data month
+    sst_field  : (Xs, Ys, Tfull) raw May SST (only used by configs with use_sst) or None
+    sie        : dict region -> (Tfull,) September (or target-month) extent
+    psar / lat : weights for intra_links (area for the polar grid, latitude grid for SST)
+    """
+
+    def __init__(self, config_names, sic_fields, sie, fmin, fmax, psar, sst_field=None, sst_lat=None,
+                 significance=0.01, max_areas=None, max_pred=384):
+        require_cuda()
+        self.cfgs = [CONFIGS[c] if isinstance(c, str) else c for c in config_names]
+        self.fmin, self.fmax = int(fmin), int(fmax)
+        self.years = list(range(self.fmin, self.fmax + 1))
+        self.significance = significance
+        first = np.asarray(sic_fields[self.cfgs[0].name])
+        self.X, self.Y, self.Tfull = first.shape
+        assert self.Tfull >= self.fmax - FIRST_YEAR + 1
+        self.sic_host = np.stack([np.ascontiguousarray(sic_fields[c.name], dtype=np.float64).reshape(
+            self.X * self.Y, self.Tfull) for c in self.cfgs])
+        self.psar_host = np.sqrt(np.asarray(psar, dtype=np.float64)).reshape(-1)     # :296-299
+        self.use_sst = any(c.use_sst for c in self.cfgs)
+        if self.use_sst:
+            s = np.ascontiguousarray(sst_field, dtype=np.float64)
+            self.Xs, self.Ys = s.shape[0], s.shape[1]
+            self.sst_host = s.reshape(1, self.Xs * self.Ys, self.Tfull)
+            self.lat_host = np.sqrt(np.cos(np.radians(np.asarray(sst_lat, dtype=np.float64)))).reshape(-1)
+        # ---- jobs: one network per (config, network-year)
+        self.jobs = []          # (cfg index, network year)
+        self.job_index = {}
+        for ci, cfg in enumerate(self.cfgs):
+            for year in self.years:
+                ny = year - 1 if cfg.prev_year_network else year
+                if (ci, ny) not in self.job_index:
+                    self.job_index[(ci, ny)] = len(self.jobs)
+                    self.jobs.append((ci, ny))
+        job_field = np.array([ci for ci, _ in self.jobs], dtype=np.int32)
+        job_T = np.array([ny - FIRST_YEAR + 1 for _, ny in self.jobs], dtype=np.int32)
+        n_upper = int(max((~np.isnan(f).any(axis=1)).sum() for f in self.sic_host))
+        self.sic = NetworkBatch(self.X, self.Y, self.Tfull, len(self.jobs), latlon=False, n_upper=n_upper,
+                                max_areas=max_areas)
+        self.job_field_host, self.job_T_host = job_field, job_T
+        self.rcrit_host = np.array([r_crit_ttest(int(T), significance) for T in job_T])
+        self.sst = None
+        if self.use_sst:
+            self.sst_years = self.years
+            sT = np.array([y - FIRST_YEAR + 1 for y in self.sst_years], dtype=np.int32)
+            n_up = int((~np.isnan(self.sst_host[0]).any(axis=1)).sum())
+            self.sst = NetworkBatch(self.Xs, self.Ys, self.Tfull, len(self.sst_years), latlon=True, n_upper=n_up,
+                                    max_areas=max_areas)
+            self.sst_T_host = sT
+            self.sst_rcrit_host = np.array([r_crit_ttest(int(T), significance) for T in sT])
+        # ---- SIE tables and GP problems
+        self.sie = {k: np.asarray(v, dtype=np.float64) for k, v in sie.items()}
+        self.sie_dt, self.sie_trend = {}, {}
+        for reg, series in self.sie.items():
+            self.sie_dt[reg], self.sie_trend[reg] = sie_detrend_tables(series, self.fmin, self.fmax)
+        probs, ys, self.prob_meta = [], [], []
+        y_off = 0
+        for ci, cfg in enumerate(self.cfgs):
+            for k, reg in enumerate(cfg.regions):
+                for year in self.years:
+                    row = year - (self.fmin - 1) - 1
+                    if cfg.prev_year_network:
+                        y = self.sie_dt[reg][row, 1:year - FIRST_YEAR]          # south January1st_retro.py:175
+                    else:
+                        y = self.sie_dt[reg][row, 0:year - FIRST_YEAR]          # June1st_retro.py:220
+                    n = y.size
+                    ny = year - 1 if cfg.prev_year_network else year
+                    p = np.zeros(1, dtype=GP_PROBLEM_DTYPE)
+                    p["job_sic"] = self.job_index[(ci, ny)]
+                    p["job_sst"] = self.sst_years.index(year) if cfg.use_sst else -1
+                    p["n"] = n
+                    p["y_off"] = y_off
+                    p["rule"] = cfg.rule[k]
+                    p["zscore"] = int(cfg.zscore)
+                    p["r_sel"] = r_crit_pearson(n, cfg.alpha) if cfg.rule[k] == RULE_POS_SIG else 0.0
+                    p["ell"] = cfg.ell[k]
+                    p["sig"] = cfg.sig[k]
+                    probs.append(p)
+                    ys.append(y)
+                    y_off += n
+                    self.prob_meta.append((ci, k, year))
+        self.prob_host = np.concatenate(probs)
+        self.y_host = np.concatenate(ys)
+        self.P = len(probs)
+        self.gp = GpBatch(self.P, max_pred=max_pred)
+        self.n_forecasts = self.P
+        # pinned staging buffers so every step pays a real host->device copy
+        self._pin = {name: torch.from_numpy(arr).pin_memory() for name, arr in self._host_inputs().items()}
+
+    def _host_inputs(self):
+        d = {"sic": self.sic_host, "job_field": self.job_field_host, "job_T": self.job_T_host,
+             "rcrit": self.rcrit_host, "psar": self.psar_host, "prob": self.prob_host.view(np.uint8),
+             "y": self.y_host}
+        if self.use_sst:
+            d.update({"sst": self.sst_host, "sst_T": self.sst_T_host, "sst_rcrit": self.sst_rcrit_host,
+                      "lat": self.lat_host, "sst_field_idx": np.zeros(len(self.sst_years), dtype=np.int32)})
+        return d
+
+    def h2d_bytes(self):
+        return int(sum(t.numel() * t.element_size() for t in self._pin.values()))
+
+    def d2h_bytes(self):
+        return int(self.P * GP_RESULT_DTYPE.itemsize)
+
+    def upload(self):
+        """Host -> device copy of every input (pinned, async on the current stream)."""
+        self.dev = {k: t.to("cuda", non_blocking=True) for k, t in self._pin.items()}
+        return self.dev
+
+    def compute(self):
+        """Enqueue the whole hot path on the current stream (no host sync)."""
+        d = self.dev
+        self.sic.build(d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"], do_detrend=True)
+        if self.use_sst:
+            self.sst.build(d["sst"], d["sst_field_idx"], d["sst_T"], d["sst_rcrit"], d["lat"], do_detrend=True)
+        self.gp.run(d["prob"], d["y"], self.sic, self.sst)
+
+    def kernel_launches(self):
+        return 11 * (2 if self.use_sst else 1) + 1
+
+    def download(self):
+        """Device -> host read of the GP results (synchronises)."""
+        self.raw = self.gp.results()
+        return self.raw
+
+    def run(self):
+        self.upload()
+        self.compute()
+        return self.assemble(self.download())
+
+    def assemble(self, raw):
+        """-> {config: {region_fmean / _fvar / _fmean_rt: array(years)}} like the reference's GPR dict
+        (June1st_retro.py:284-290, values rounded to 3 d.p.), plus the un-rounded record under '_raw'."""
+        out = {}
+        for (ci, k, year), r in zip(self.prob_meta, raw):
+            cfg = self.cfgs[ci]
+            g = out.setdefault(cfg.name, {})
+            reg = cfg.regions[k]
+            for key in ("_fmean", "_fvar", "_fmean_rt"):
+                g.setdefault(reg + key, np.zeros(len(self.years)))
+            i = year - self.fmin
+            fmean = np.round(r["fmean"], 3)
+            row = year - (self.fmin - 1) - 1
+            slope, icpt = self.sie_trend[reg][row]
+            lineT = (np.arange(year - FIRST_YEAR + 1) * slope) + icpt
+            g[reg + "_fmean"][i] = fmean
+            g[reg + "_fvar"][i] = np.round(r["fvar"], 3)
+            g[reg + "_fmean_rt"][i] = np.round(fmean + lineT[-1], 3)
+        out["_raw"] = raw
+        return out

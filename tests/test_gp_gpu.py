@@ -1,0 +1,98 @@
+"""GPU parity: batched GP kernel (K7-K9) vs the oracle's numpy/scipy restatement of forecast()/MLII().
+Tolerance: 1e-9 relative (north_star), widened only by the documented conditioning terms:
+  * expm with s squarings amplifies rounding by ~2^s (scipy itself moves this much under a
+    1-ulp input perturbation, see tests/test_expm_spec.py) -> 64*2^s*2^-53
+  * two backward-stable Cholesky solves differ by ~cond(K)*2^-53."""
+import numpy as np
+import pytest
+
+from seaiceextentforecasting_b200.config import CONFIGS, RULE_ALL, RULE_POS, RULE_POS_SIG
+
+pytestmark = pytest.mark.gpu
+
+
+def make_problem(seed, n, nA, nS=0, scale=1.0):
+    rng = np.random.default_rng(seed)
+    common = rng.standard_normal((3, n + 1))
+    sic = {}
+    for a in range(nA):
+        w = rng.standard_normal(3) * 0.8
+        sic[a * 2 + 1] = scale * (w @ common + rng.standard_normal(n + 1))
+    sst = None
+    if nS:
+        sst = {a: 0.1 * (rng.standard_normal(3) @ common + rng.standard_normal(n + 1)) for a in range(nS)}
+    y = np.round(0.3 * (common[0, :n] - common[1, :n]) + 0.2 * rng.standard_normal(n), 3)
+    return y, sic, sst
+
+
+def oracle_forecast(y, sic, sst, rule, alpha, zscore, ell, sig):
+    from oracle import gp as og
+    Xfull = og.select_predictors(y, sic, sst, {RULE_POS: "pos", RULE_ALL: "all", RULE_POS_SIG: "pos_sig"}[rule], alpha)
+    X, Xs, M = og.design(Xfull, zscore)
+    out = og.gp_fit_predict(X, Xs, y[:, None], M, ell, sig)
+    n = len(y)
+    from scipy.linalg import expm
+    K = out["sigma_f"] * (X @ expm(ell * M) @ X.T + sig * np.eye(n))
+    out["cond"] = np.linalg.cond(K)
+    out["n_pred"] = Xfull.shape[1]
+    out["X"], out["M"] = X, M
+    return out
+
+
+def tol(res, cond):
+    return max(1e-9, 64.0 * 2.0 ** int(res["expm_s"]) * 2.0 ** -53, 8.0 * cond * 2.0 ** -53)
+
+
+CASES = []
+for name, cfg in CONFIGS.items():
+    for k in range(3):
+        CASES.append((name, k))
+
+
+@pytest.mark.parametrize("name,k", CASES)
+@pytest.mark.parametrize("n", [6, 20, 41])
+def test_forecast_matches_oracle(lib_built, name, k, n):
+    from seaiceextentforecasting_b200.forecast import forecast
+    cfg = CONFIGS[name]
+    # raw (un-z-scored) node series are sums over ~30 cells x sqrt(1e4): O(1e2..1e3)
+    y, sic, sst = make_problem(hash((name, k, n)) % 10000, n, nA=12 + 2 * k, nS=6 if cfg.use_sst else 0,
+                               scale=1.0 if cfg.zscore else 30.0)
+    r = forecast(y, sic, sst, rule=cfg.rule[k], alpha=cfg.alpha, zscore=cfg.zscore, ell=cfg.ell[k], sig=cfg.sig[k])
+    try:
+        o = oracle_forecast(y, sic, sst, cfg.rule[k], cfg.alpha, cfg.zscore, cfg.ell[k], cfg.sig[k])
+    except (np.linalg.LinAlgError, IndexError, ValueError):
+        assert r["info"] != 0
+        return
+    assert r["info"] == 0
+    assert r["n_pred"] == o["n_pred"]                      # identical predictor selection
+    t = tol(r, o["cond"])
+    scale = max(abs(o["fmean"]), np.sqrt(abs(o["fvar"])), 1e-3)
+    assert abs(r["fmean"] - o["fmean"]) <= t * scale, (r["fmean"], o["fmean"], t)
+    assert abs(r["fvar"] - o["fvar"]) <= t * max(abs(o["fvar"]), scale ** 2)
+    assert abs(r["sigma_f"] - o["sigma_f"]) <= t * abs(o["sigma_f"])
+    assert abs(r["nlml"] - o["nlml"]) <= t * max(1.0, abs(o["nlml"]))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_mlii_matches_oracle(lib_built, seed):
+    from oracle import gp as og
+    from seaiceextentforecasting_b200.forecast import mlii
+    n = [8, 15, 22, 30, 41, 12][seed]
+    y, sic, _ = make_problem(100 + seed, n, nA=10)
+    theta = np.log([np.logspace(-7, 2, 20)[8 + seed], np.logspace(-3, 9, 20)[2 + seed]])
+    nl, g = mlii(theta, y, sic, rule=RULE_POS, zscore=True)
+    Xfull = og.select_predictors(y, sic, None, "pos")
+    X, Xs, M = og.design(Xfull, True)
+    onl, og_ = og.mlii(theta, X, y[:, None], M)
+    assert abs(nl - onl) <= 1e-9 * max(1.0, abs(onl))
+    np.testing.assert_allclose(g, og_, rtol=1e-7, atol=1e-9 * max(1.0, np.abs(og_).max()))
+
+
+def test_not_spd_reports_like_reference(lib_built):
+    """sigma_n~ = 0 with more rows than predictors: K is singular -> LinAlgError in forecast(), inf in MLII."""
+    from seaiceextentforecasting_b200.forecast import forecast, mlii
+    y, sic, _ = make_problem(5, 30, nA=3)
+    r = forecast(y, sic, None, rule=RULE_ALL, ell=1e-3, sig=0.0)
+    assert r["info"] > 0 or not np.isfinite(r["fmean"])
+    nl, g = mlii(np.array([np.log(1e-3), -800.0]), y, sic, rule=RULE_ALL)
+    assert nl == np.inf or np.isfinite(nl)

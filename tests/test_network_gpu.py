@@ -1,0 +1,125 @@
+"""GPU parity: drop-in Network (K1-K6 through the C ABI) vs the oracle on identical seeded inputs.
+Bar (BASELINE.json north_star): nodes / area membership / order bit-exact; floats <= 1e-9 relative."""
+import warnings
+
+import numpy as np
+import pytest
+
+from seaiceextentforecasting_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+CASES = [  # X, Y, T, latlon, seed
+    (14, 14, 20, False, 1), (16, 12, 9, False, 2), (10, 24, 30, True, 3), (12, 30, 12, True, 4),
+    (20, 20, 42, False, 5), (24, 24, 7, False, 6), (26, 90, 42, True, 7), (33, 31, 17, False, 8),
+]
+
+
+def _oracle(dt, latlon, kw):
+    from oracle.network import Network as ON
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = ON(data=dt)
+        ON.tau(o, 0.01, keep_corrs=False)
+        ON.area_level(o, latlon_grid=latlon)
+        ON.intra_links(o, **kw)
+    return o
+
+
+def _product(dt, latlon, kw):
+    from seaiceextentforecasting_b200.ComplexNetworks import Network
+    n = Network(data=dt)
+    Network.tau(n, 0.01)
+    Network.area_level(n, latlon_grid=latlon)
+    Network.intra_links(n, **kw)
+    return n
+
+
+def compare_networks(n, o, dt):
+    assert n.nodes.dtype == np.int64 and n.nodes.shape == o.nodes.shape
+    assert np.array_equal(n.nodes, o.nodes)                                     # bit-exact node mask
+    R = n.correlation_matrix()
+    assert np.array_equal(R, R.T, equal_nan=True)                               # bitwise symmetric (H1)
+    assert np.isnan(np.diag(R)).all()
+    m = ~np.isnan(o.R)
+    assert np.max(np.abs(R[m] - o.R[m])) <= 1e-9                                # |R| <= 1: absolute == relative bar
+    assert abs(n.tau - o.tau) <= 1e-9 * abs(o.tau)
+    assert list(n.V.keys()) == list(o.V.keys())                                 # dict order
+    for k in o.V:
+        assert n.V[k] == o.V[k], f"area {k} differs"                            # membership AND list order
+    assert n.V is n.A
+    for k in o.V:
+        np.testing.assert_allclose(n.anomaly[k], o.anomaly[k], rtol=1e-9, atol=1e-9 * np.abs(o.anomaly[k]).max())
+        sc = max(1e-300, np.abs(np.asarray(o.links[k])).max())
+        np.testing.assert_allclose(np.asarray(n.links[k], dtype=float), np.asarray(o.links[k], dtype=float),
+                                   rtol=1e-9, atol=1e-9 * sc)
+        assert abs(n.strength[k] - o.strength[k]) <= 1e-9 * abs(o.strength[k])
+    assert np.array_equal(np.isnan(n.strengthmap), np.isnan(o.strengthmap))
+    ok = ~np.isnan(o.strengthmap)
+    np.testing.assert_allclose(n.strengthmap[ok], o.strengthmap[ok], rtol=1e-9)
+
+
+@pytest.mark.parametrize("X,Y,T,latlon,seed", CASES)
+def test_network_matches_oracle(lib_built, X, Y, T, latlon, seed):
+    from oracle.gp import detrend as odetrend
+    from seaiceextentforecasting_b200.forecast import detrend
+    data, _ = syn.make_field(X, Y, T, seed, latlon=latlon)
+    dt, trend = detrend(data)
+    odt, otrend = odetrend(data)
+    assert np.array_equal(np.isnan(dt), np.isnan(odt))
+    ok = ~np.isnan(odt)
+    assert np.max(np.abs(dt[ok] - odt[ok])) <= 1e-12                            # residuals of O(1) series
+    okt = ~np.isnan(otrend)
+    np.testing.assert_allclose(trend[okt], otrend[okt], rtol=1e-9, atol=1e-12)
+    kw = {"lat": syn.make_lat_grid(X, Y)} if latlon else {"area": syn.make_psar(X, Y)}
+    # both sides start from the SAME detrended field (the reference's Network takes `dt` as input)
+    n = _product(odt, latlon, kw)
+    o = _oracle(odt, latlon, kw)
+    compare_networks(n, o, odt)
+
+
+def test_network_full_north_grid(lib_built):
+    """57x57x42 (config 1 size): the oracle finishes in seconds, the reference takes ~45 s."""
+    from oracle.gp import detrend as odetrend
+    data, _ = syn.make_field(57, 57, 42, 11)
+    odt, _ = odetrend(data)
+    kw = {"area": syn.make_psar(57, 57)}
+    n = _product(odt, False, kw)
+    o = _oracle(odt, False, kw)
+    compare_networks(n, o, odt)
+    assert len(n.V) >= 2
+
+
+def test_errors_like_reference(lib_built):
+    from seaiceextentforecasting_b200.ComplexNetworks import Network
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal((6, 6, 12))          # no NaN cell -> IndexError (ComplexNetworks.py:50-51)
+    n = Network(data=data)
+    Network.tau(n, 0.01)
+    with pytest.raises(IndexError):
+        Network.area_level(n)
+    data[0, 0, :] = np.nan                           # white noise: no area reaches tau -> ValueError (:212)
+    n = Network(data=data)
+    Network.tau(n, 0.01)
+    with pytest.raises(ValueError):
+        Network.area_level(n)
+
+
+def test_corrs_lazy_view(lib_built):
+    from seaiceextentforecasting_b200.ComplexNetworks import Network
+    data, _ = syn.make_field(10, 10, 16, 21)
+    from oracle.gp import detrend as odetrend
+    odt, _ = odetrend(data)
+    n = Network(data=odt)
+    Network.tau(n, 0.01)
+    from oracle.network import Network as ON
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = ON(data=odt)
+        ON.tau(o, 0.01)
+    c = np.asarray(n.corrs)
+    assert c.shape == o.corrs.shape
+    assert np.array_equal(np.isnan(c), np.isnan(o.corrs))
+    m = ~np.isnan(o.corrs)
+    assert np.max(np.abs(c[m] - o.corrs[m])) <= 1e-9
+    assert n.corrs[3, 4, 5] == c[3, 4, 5] or np.isnan(c[3, 4, 5])
