@@ -102,13 +102,15 @@ int sie_corr_stencil(const double* R, const int32_t* node_cell, const int32_t* c
  * status     [B]  SIE_JOB_* (areas are still written when status == SIE_JOB_FEW_AREAS, like the
  *            reference leaves V populated when it raises at :278)
  * scratch    at least sie_area_level_scratch_bytes(B, X*Y) bytes
+ * work       [B][4] or NULL: per job {correlations consumed (the algorithmic gather count, 8 B each),
+ *            SM cycles in step 1, SM cycles in step 2, (growth steps << 32) | merge rounds}
  */
 int sie_area_level(const double* R, const double* stencil, const int32_t* node_cell,
                    const int32_t* cell_node, const int32_t* n_nodes, const double* tau,
                    const int32_t* first_nan_cell, int B, int X, int Y, int ldn, int latlon,
                    int max_areas, int32_t* area_cells, int32_t* area_start, int32_t* area_key,
                    int32_t* n_areas, int32_t* label, int32_t* status,
-                   void* scratch, size_t scratch_bytes, void* stream);
+                   void* scratch, size_t scratch_bytes, uint64_t* work, void* stream);
 size_t sie_area_level_scratch_bytes(int B, int C);
 
 /* ---------------------------------------------------------------------------------------------
@@ -135,7 +137,7 @@ int sie_intra_links(const double* dt, const double* scale, const int32_t* job_T,
  *   y            y_all + prob[p].y_off, n = prob[p].n training targets
  *   predictors   up to two series sets (SIC, SST): set s has n_areas[job_s] series of length n+1 at
  *                anomaly + (job_s*max_areas + a)*Tstride
- * and writes out[p] = {fmean, fvar, sigma_f, nlml, g_ell, g_sig, n_pred, expm_m, expm_s, info}.
+ * and writes out[p] = {fmean, fvar, sigma_f, nlml, g_ell, g_sig, n_pred, expm_m, expm_s, info, cycles...}.
  */
 typedef struct SieGpProblem {
   int32_t job_sic;      /* index into the first anomaly set (required) */
@@ -154,6 +156,7 @@ typedef struct SieGpProblem {
 typedef struct SieGpResult {
   double fmean, fvar, sigma_f, nlml, g_ell, g_sig;
   int32_t n_pred, expm_m, expm_s, info; /* info: 0 ok, k>0 Cholesky failed at pivot k, -1 no predictors, -2 capacity */
+  int64_t cycles_total, cycles_expm;    /* SM cycles this problem took (whole / expm only), for profiling */
 } SieGpResult;
 
 int sie_gp_forecast(const SieGpProblem* prob, int P, const double* y_all,

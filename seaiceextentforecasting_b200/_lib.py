@@ -25,7 +25,7 @@ class SieGpProblem(C.Structure):
 class SieGpResult(C.Structure):
     _fields_ = [("fmean", C.c_double), ("fvar", C.c_double), ("sigma_f", C.c_double), ("nlml", C.c_double),
                 ("g_ell", C.c_double), ("g_sig", C.c_double), ("n_pred", c_i32), ("expm_m", c_i32),
-                ("expm_s", c_i32), ("info", c_i32)]
+                ("expm_s", c_i32), ("info", c_i32), ("cycles_total", C.c_int64), ("cycles_expm", C.c_int64)]
 
 
 _SIGS = {
@@ -39,7 +39,7 @@ _SIGS = {
     "sie_corr_tau_scratch_bytes": (c_sz, [C.c_int, C.c_int]),
     "sie_corr_stencil": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p]),
     "sie_area_level": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                 C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+                                 C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p, c_p]),
     "sie_area_level_scratch_bytes": (c_sz, [C.c_int, C.c_int]),
     "sie_intra_links": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p,
                                   c_p, c_p, c_p]),

@@ -109,10 +109,13 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
              int32_t* __restrict__ area_cells_all, int32_t* __restrict__ area_start_all,
              int32_t* __restrict__ area_key_all, int32_t* __restrict__ n_areas_all,
              int32_t* __restrict__ label_all, int32_t* __restrict__ status_all,
-             unsigned char* __restrict__ scratch_all, size_t scratch_stride, int use_smem) {
+             unsigned char* __restrict__ scratch_all, size_t scratch_stride, int use_smem,
+             unsigned long long* __restrict__ work_all) {
   extern __shared__ __align__(16) int32_t smem_i[];
   __shared__ Best slots[NT / 32];
   __shared__ int sh_i[8];
+  __shared__ unsigned long long sh_work;
+  unsigned long long wk = 0;   // correlations consumed (algorithmic gathers), tallied by lane 0 of each group
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -138,7 +141,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   int32_t* hc = ib + 4 * C;               // [C] cell list of the best area (step 2)
 
   for (int c = tid; c < C; c += NT) { lab[c] = -1; fkey[c] = NOKEY; out_label[c] = -1; }
-  if (tid == 0) { n_areas_all[b] = 0; out_start[0] = 0; }
+  if (tid == 0) { n_areas_all[b] = 0; out_start[0] = 0; sh_work = 0ull; if (work_all) work_all[4 * b] = 0ull; }
   __syncthreads();
   if (first_nan_cell[b] < 0) {            // :50-51 IndexError in the reference
     if (tid == 0) status_all[b] = SIE_JOB_NO_NAN_CELL;
@@ -147,6 +150,8 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   if (status_all[b] == SIE_JOB_CAPACITY) return;   // K1 already flagged this job
 
   // =============================================================== step 1 (:154-196)
+  const long long clk0 = clock64();
+  unsigned long long n_steps = 0, n_rounds = 0;
   int nA = 0;        // areas created so far (uniform across the CTA)
   int base = 0;      // cells assigned so far
   bool overflow = false;
@@ -235,6 +240,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         const double* row = R + (size_t)cnode[f] * ldn;
         int nanc = 0;
         const double sum = sie_pw_sum8([&](int i) { return __ldg(row + hn[i]); }, n, j, gmask, nanc);
+        if (j == 0) wk += (unsigned long long)n;
         nanc += __shfl_xor_sync(gmask, nanc, 1);
         nanc += __shfl_xor_sync(gmask, nanc, 2);
         nanc += __shfl_xor_sync(gmask, nanc, 4);
@@ -271,6 +277,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
       __syncthreads();
       nf = sh_i[1];
       ++n;
+      ++n_steps;
     }
     __syncthreads();
     for (int q = tid; q < nf; q += NT) fkey[flist[q]] = NOKEY;
@@ -288,6 +295,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   }
 
   // =============================================================== step 2 (:200-265)
+  const long long clk1 = clock64();
   // `taken` is now "belongs to a finalised area"; lab[] keeps tracking the current owner key.
   int cur_best = -1, nb = 0;     // best area whose lists are materialised in hn/hc
   const size_t RM = rm_cap(C);
@@ -309,6 +317,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
     const Best bw = block_best(loc, slots);
     if (bw.idx < 0 || bw.mean == 0.0) break;   // no areas at all (ValueError at :212) or all finalised
     const int best = bw.idx;
+    ++n_rounds;
     if (best != cur_best) {                    // materialise V[best] in list order
       int off = 0;
       for (int s = best; s >= 0; s = S.seg_next[s]) {
@@ -385,6 +394,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
             int nanc = 0;
             double sum = 0.0;
             if (len > 0) {
+              if (j == 0) wk += (unsigned long long)len;
               sum = sie_pw_sum8(
                   [&](int i) { const int t = p + 1 + i; return __ldg(row + ((t < nb) ? hn[t] : kn[t - nb])); },
                   len, j, gmask, nanc);
@@ -478,7 +488,15 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   }
 
   // =============================================================== output in dict order (ascending key)
+  if (wk) atomicAdd(&sh_work, wk);
   __syncthreads();
+  if (tid == 0 && work_all) {
+    const long long clk2 = clock64();
+    work_all[4 * b] = sh_work;                                  // correlations consumed
+    work_all[4 * b + 1] = (unsigned long long)(clk1 - clk0);    // SM cycles in step 1
+    work_all[4 * b + 2] = (unsigned long long)(clk2 - clk1);    // SM cycles in step 2
+    work_all[4 * b + 3] = (n_steps << 32) | n_rounds;           // growth steps, merge rounds
+  }
   if (tid == 0) {
     int cnt = 0, off = 0;
     for (int k = 0; k < nA; ++k) {
@@ -523,7 +541,7 @@ extern "C" int sie_area_level(const double* R, const double* stencil, const int3
                               const int32_t* first_nan_cell, int B, int X, int Y, int ldn, int latlon,
                               int max_areas, int32_t* area_cells, int32_t* area_start, int32_t* area_key,
                               int32_t* n_areas, int32_t* label, int32_t* status, void* scratch,
-                              size_t scratch_bytes, void* stream) {
+                              size_t scratch_bytes, uint64_t* work, void* stream) {
   SIE_CHECK_ARG(R && stencil && node_cell && cell_node && n_nodes && tau && first_nan_cell && area_cells &&
                     area_start && area_key && n_areas && label && status && scratch, "null pointer");
   SIE_CHECK_ARG(B > 0 && X > 0 && Y > 0 && ldn > 0 && max_areas > 0, "non-positive size");
@@ -541,7 +559,8 @@ extern "C" int sie_area_level(const double* R, const double* stencil, const int3
   cudaFuncSetAttribute(k_area_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_area_level<<<B, NT, smem, (cudaStream_t)stream>>>(
       R, stencil, node_cell, cell_node, n_nodes, tau, first_nan_cell, X, Y, ldn, latlon, max_areas, area_cells,
-      area_start, area_key, n_areas, label, status, (unsigned char*)scratch, per_job, use_smem);
+      area_start, area_key, n_areas, label, status, (unsigned char*)scratch, per_job, use_smem,
+      (unsigned long long*)work);
   SIE_CHECK_LAUNCH();
   return SIE_OK;
 }

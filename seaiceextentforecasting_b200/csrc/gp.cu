@@ -418,6 +418,8 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
     SieGpResult res;
     res.fmean = res.fvar = res.sigma_f = res.nlml = res.g_ell = res.g_sig = sie_nan();
     res.n_pred = 0; res.expm_m = 0; res.expm_s = 0; res.info = 0;
+    res.cycles_total = 0; res.cycles_expm = 0;
+    const long long clk_start = clock64();
     __syncthreads();
     if (n < 2 || n + 1 > MAXN) {
       if (tid == 0) { res.info = -2; out[p] = res; }
@@ -528,8 +530,10 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
     }
     __syncthreads();
     int em = 0, es = 0;
+    const long long clk_e0 = clock64();
     const double* E = cta_expm(buf, ld, np_, v0, v1, &em, &es, sm);
     res.expm_m = em; res.expm_s = es;
+    res.cycles_expm = clock64() - clk_e0;
     // ---- W = X Sigma~ X^T : XE = X E (n x Np), then W = XE X^T (n x n, shared)
     cta_gemm(XE, ld, Xg, ld, E, ld, n, np_, np_, sm);
     for (int idx = tid; idx < n * n; idx += GT) {
@@ -650,7 +654,7 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
         __syncthreads();
       }
     }
-    if (tid == 0) out[p] = res;
+    if (tid == 0) { res.cycles_total = clock64() - clk_start; out[p] = res; }
   }
 }
 

@@ -24,7 +24,7 @@ GP_PROBLEM_DTYPE = np.dtype([("job_sic", "<i4"), ("job_sst", "<i4"), ("n", "<i4"
                              ("r_sel", "<f8"), ("ell", "<f8"), ("sig", "<f8")])
 GP_RESULT_DTYPE = np.dtype([("fmean", "<f8"), ("fvar", "<f8"), ("sigma_f", "<f8"), ("nlml", "<f8"),
                             ("g_ell", "<f8"), ("g_sig", "<f8"), ("n_pred", "<i4"), ("expm_m", "<i4"),
-                            ("expm_s", "<i4"), ("info", "<i4")])
+                            ("expm_s", "<i4"), ("info", "<i4"), ("cycles_total", "<i8"), ("cycles_expm", "<i8")])
 assert GP_PROBLEM_DTYPE.itemsize == C.sizeof(_lib.SieGpProblem)
 assert GP_RESULT_DTYPE.itemsize == C.sizeof(_lib.SieGpResult)
 
@@ -174,105 +174,159 @@ def mlii(theta, y, anoms_sic, anoms_sst=None, rule=0, alpha=0.05, zscore=False):
 # ------------------------------------------------------------------------------------------------
 # retrospective sweep
 # ------------------------------------------------------------------------------------------------
-class RetrospectiveSweep:
-    """years fmin..fmax x the given init-month configs x 3 regions, in one device-resident batch.
+class SweepPlan:
+    """Host-only bookkeeping of a retrospective sweep: which network builds (jobs) and which GP problems exist,
+    in the year/row indexing of the reference scripts (June1st_retro.py:199-290; south January1st_retro.py:173-182
+    for the previous-year variant).  `rank`/`world` shard whole (config, year) tasks -- a task owns its network
+    build(s) and its three regional forecasts, so shards exchange nothing."""
 
-    sic_fields : dict config-name -> (X, Y, Tfull) raw monthly SIC of that init's data month
-    sst_field  : (Xs, Ys, Tfull) raw May SST (only used by configs with use_sst) or None
-    sie        : dict region -> (Tfull,) September (or target-month) extent
-    psar / lat : weights for intra_links (area for the polar grid, latitude grid for SST)
-    """
-
-    def __init__(self, config_names, sic_fields, sie, fmin, fmax, psar, sst_field=None, sst_lat=None,
-                 significance=0.01, max_areas=None, max_pred=384):
-        require_cuda()
+    def __init__(self, config_names, sie, fmin, fmax, significance=0.01, rank=0, world=1):
         self.cfgs = [CONFIGS[c] if isinstance(c, str) else c for c in config_names]
         self.fmin, self.fmax = int(fmin), int(fmax)
         self.years = list(range(self.fmin, self.fmax + 1))
         self.significance = significance
-        first = np.asarray(sic_fields[self.cfgs[0].name])
-        self.X, self.Y, self.Tfull = first.shape
-        assert self.Tfull >= self.fmax - FIRST_YEAR + 1
-        self.sic_host = np.stack([np.ascontiguousarray(sic_fields[c.name], dtype=np.float64).reshape(
-            self.X * self.Y, self.Tfull) for c in self.cfgs])
-        self.psar_host = np.sqrt(np.asarray(psar, dtype=np.float64)).reshape(-1)     # :296-299
+        self.rank, self.world = int(rank), int(world)
         self.use_sst = any(c.use_sst for c in self.cfgs)
-        if self.use_sst:
-            s = np.ascontiguousarray(sst_field, dtype=np.float64)
-            self.Xs, self.Ys = s.shape[0], s.shape[1]
-            self.sst_host = s.reshape(1, self.Xs * self.Ys, self.Tfull)
-            self.lat_host = np.sqrt(np.cos(np.radians(np.asarray(sst_lat, dtype=np.float64)))).reshape(-1)
-        # ---- jobs: one network per (config, network-year)
-        self.jobs = []          # (cfg index, network year)
-        self.job_index = {}
-        for ci, cfg in enumerate(self.cfgs):
-            for year in self.years:
-                ny = year - 1 if cfg.prev_year_network else year
-                if (ci, ny) not in self.job_index:
-                    self.job_index[(ci, ny)] = len(self.jobs)
-                    self.jobs.append((ci, ny))
-        job_field = np.array([ci for ci, _ in self.jobs], dtype=np.int32)
-        job_T = np.array([ny - FIRST_YEAR + 1 for _, ny in self.jobs], dtype=np.int32)
-        n_upper = int(max((~np.isnan(f).any(axis=1)).sum() for f in self.sic_host))
-        self.sic = NetworkBatch(self.X, self.Y, self.Tfull, len(self.jobs), latlon=False, n_upper=n_upper,
-                                max_areas=max_areas)
-        self.job_field_host, self.job_T_host = job_field, job_T
-        self.rcrit_host = np.array([r_crit_ttest(int(T), significance) for T in job_T])
-        self.sst = None
-        if self.use_sst:
-            self.sst_years = self.years
-            sT = np.array([y - FIRST_YEAR + 1 for y in self.sst_years], dtype=np.int32)
-            n_up = int((~np.isnan(self.sst_host[0]).any(axis=1)).sum())
-            self.sst = NetworkBatch(self.Xs, self.Ys, self.Tfull, len(self.sst_years), latlon=True, n_upper=n_up,
-                                    max_areas=max_areas)
-            self.sst_T_host = sT
-            self.sst_rcrit_host = np.array([r_crit_ttest(int(T), significance) for T in sT])
-        # ---- SIE tables and GP problems
+        # tasks in a fixed global order, longest windows first so round-robin shards are balanced
+        tasks = [(ci, year) for year in reversed(self.years) for ci in range(len(self.cfgs))]
+        self.all_tasks = tasks
+        self.tasks = [t for i, t in enumerate(tasks) if i % self.world == self.rank]
+        self.jobs, self.job_index = [], {}          # SIC network builds: (cfg index, network year)
+        self.sst_years = []                         # SST network builds (one per target year that needs it)
+        for ci, year in self.tasks:
+            cfg = self.cfgs[ci]
+            ny = year - 1 if cfg.prev_year_network else year
+            if (ci, ny) not in self.job_index:
+                self.job_index[(ci, ny)] = len(self.jobs)
+                self.jobs.append((ci, ny))
+            if cfg.use_sst and year not in self.sst_years:
+                self.sst_years.append(year)
+        self.job_field = np.array([ci for ci, _ in self.jobs], dtype=np.int32)
+        self.job_T = np.array([ny - FIRST_YEAR + 1 for _, ny in self.jobs], dtype=np.int32)
+        self.rcrit = np.array([r_crit_ttest(int(T), significance) for T in self.job_T])
+        self.sst_T = np.array([y - FIRST_YEAR + 1 for y in self.sst_years], dtype=np.int32)
+        self.sst_rcrit = np.array([r_crit_ttest(int(T), significance) for T in self.sst_T])
         self.sie = {k: np.asarray(v, dtype=np.float64) for k, v in sie.items()}
         self.sie_dt, self.sie_trend = {}, {}
         for reg, series in self.sie.items():
             self.sie_dt[reg], self.sie_trend[reg] = sie_detrend_tables(series, self.fmin, self.fmax)
         probs, ys, self.prob_meta = [], [], []
         y_off = 0
-        for ci, cfg in enumerate(self.cfgs):
+        for ci, year in self.tasks:
+            cfg = self.cfgs[ci]
             for k, reg in enumerate(cfg.regions):
-                for year in self.years:
-                    row = year - (self.fmin - 1) - 1
-                    if cfg.prev_year_network:
-                        y = self.sie_dt[reg][row, 1:year - FIRST_YEAR]          # south January1st_retro.py:175
-                    else:
-                        y = self.sie_dt[reg][row, 0:year - FIRST_YEAR]          # June1st_retro.py:220
-                    n = y.size
-                    ny = year - 1 if cfg.prev_year_network else year
-                    p = np.zeros(1, dtype=GP_PROBLEM_DTYPE)
-                    p["job_sic"] = self.job_index[(ci, ny)]
-                    p["job_sst"] = self.sst_years.index(year) if cfg.use_sst else -1
-                    p["n"] = n
-                    p["y_off"] = y_off
-                    p["rule"] = cfg.rule[k]
-                    p["zscore"] = int(cfg.zscore)
-                    p["r_sel"] = r_crit_pearson(n, cfg.alpha) if cfg.rule[k] == RULE_POS_SIG else 0.0
-                    p["ell"] = cfg.ell[k]
-                    p["sig"] = cfg.sig[k]
-                    probs.append(p)
-                    ys.append(y)
-                    y_off += n
-                    self.prob_meta.append((ci, k, year))
-        self.prob_host = np.concatenate(probs)
-        self.y_host = np.concatenate(ys)
+                row = year - (self.fmin - 1) - 1
+                if cfg.prev_year_network:
+                    y = self.sie_dt[reg][row, 1:year - FIRST_YEAR]          # south January1st_retro.py:175
+                else:
+                    y = self.sie_dt[reg][row, 0:year - FIRST_YEAR]          # June1st_retro.py:220
+                n = y.size
+                ny = year - 1 if cfg.prev_year_network else year
+                p = np.zeros(1, dtype=GP_PROBLEM_DTYPE)
+                p["job_sic"] = self.job_index[(ci, ny)]
+                p["job_sst"] = self.sst_years.index(year) if cfg.use_sst else -1
+                p["n"] = n
+                p["y_off"] = y_off
+                p["rule"] = cfg.rule[k]
+                p["zscore"] = int(cfg.zscore)
+                p["r_sel"] = r_crit_pearson(n, cfg.alpha) if cfg.rule[k] == RULE_POS_SIG else 0.0
+                p["ell"] = cfg.ell[k]
+                p["sig"] = cfg.sig[k]
+                probs.append(p)
+                ys.append(y)
+                y_off += n
+                self.prob_meta.append((ci, k, year))
+        self.prob = np.concatenate(probs) if probs else np.zeros(0, dtype=GP_PROBLEM_DTYPE)
+        self.y = np.concatenate(ys) if ys else np.zeros(0)
         self.P = len(probs)
-        self.gp = GpBatch(self.P, max_pred=max_pred)
-        self.n_forecasts = self.P
+
+    def assemble(self, raw, meta=None):
+        """-> {config: {region_fmean / _fvar / _fmean_rt: array(years)}} like the reference's GPR dict
+        (June1st_retro.py:284-290, rounded to 3 d.p.), the un-rounded values under '<region>_raw_*'.
+        `raw`/`meta` may be the concatenation over all ranks (after a gather)."""
+        meta = self.prob_meta if meta is None else meta
+        out = {}
+        for (ci, k, year), r in zip(meta, raw):
+            cfg = self.cfgs[ci]
+            g = out.setdefault(cfg.name, {})
+            reg = cfg.regions[k]
+            for key in ("_fmean", "_fvar", "_fmean_rt", "_raw_fmean", "_raw_fvar", "_raw_fmean_rt"):
+                g.setdefault(reg + key, np.full(len(self.years), np.nan))
+            i = year - self.fmin
+            fmean = np.round(r["fmean"], 3)
+            row = year - (self.fmin - 1) - 1
+            slope, icpt = self.sie_trend[reg][row]
+            lineT = (np.arange(year - FIRST_YEAR + 1) * slope) + icpt
+            g[reg + "_fmean"][i] = fmean
+            g[reg + "_fvar"][i] = np.round(r["fvar"], 3)
+            g[reg + "_fmean_rt"][i] = np.round(fmean + lineT[-1], 3)
+            g[reg + "_raw_fmean"][i] = r["fmean"]
+            g[reg + "_raw_fvar"][i] = r["fvar"]
+            g[reg + "_raw_fmean_rt"][i] = r["fmean"] + lineT[-1]
+        return out
+
+    def skill(self, gpr):
+        """skill() of the retro scripts (June1st_retro.py:293-314) from an assembled GPR dict."""
+        out = {}
+        for cfg in self.cfgs:
+            rt, dt_ = [], []
+            for reg in cfg.regions:
+                obs_dt = np.array([self.sie_dt[reg][t - (self.fmin - 1), t - FIRST_YEAR] for t in self.years])
+                obs_rt = self.sie[reg][self.fmin - FIRST_YEAR:self.fmax - FIRST_YEAR + 1]
+                a, b = skill(obs_rt, gpr[cfg.name][reg + "_fmean_rt"], obs_dt, gpr[cfg.name][reg + "_fmean"])
+                rt.append(a)
+                dt_.append(b)
+            out[cfg.name] = (rt, dt_)
+        return out
+
+
+class RetrospectiveSweep:
+    """years fmin..fmax x the given init-month configs x 3 regions, in one device-resident batch.
+
+    sic_fields : dict config-name -> (X, Y, Tfull) raw monthly SIC of that init's data month
+    sst_field  : (Xs, Ys, Tfull) raw May SST (only used by configs with use_sst) or None
+    sie        : dict region -> (Tfull,) September (or target-month) extent
+    psar / sst_lat : weights for intra_links (cell area for the polar grid, latitude grid for SST)
+    """
+
+    def __init__(self, config_names, sic_fields, sie, fmin, fmax, psar, sst_field=None, sst_lat=None,
+                 significance=0.01, max_areas=None, max_pred=384, rank=0, world=1):
+        require_cuda()
+        self.plan = plan = SweepPlan(config_names, sie, fmin, fmax, significance, rank, world)
+        self.cfgs, self.years, self.fmin, self.fmax = plan.cfgs, plan.years, plan.fmin, plan.fmax
+        first = np.asarray(sic_fields[self.cfgs[0].name])
+        self.X, self.Y, self.Tfull = first.shape
+        assert self.Tfull >= self.fmax - FIRST_YEAR + 1
+        self.sic_host = np.stack([np.ascontiguousarray(sic_fields[c.name], dtype=np.float64).reshape(
+            self.X * self.Y, self.Tfull) for c in self.cfgs])
+        self.psar_host = np.sqrt(np.asarray(psar, dtype=np.float64)).reshape(-1)     # ComplexNetworks.py:298-299
+        self.use_sst = plan.use_sst and len(plan.sst_years) > 0
+        n_upper = int(max((~np.isnan(f).any(axis=1)).sum() for f in self.sic_host))
+        self.sic = NetworkBatch(self.X, self.Y, self.Tfull, max(1, len(plan.jobs)), latlon=False, n_upper=n_upper,
+                                max_areas=max_areas)
+        self.sst = None
+        if self.use_sst:
+            s = np.ascontiguousarray(sst_field, dtype=np.float64)
+            self.Xs, self.Ys = s.shape[0], s.shape[1]
+            self.sst_host = s.reshape(1, self.Xs * self.Ys, self.Tfull)
+            self.lat_host = np.sqrt(np.cos(np.radians(np.asarray(sst_lat, dtype=np.float64)))).reshape(-1)  # :296-297
+            n_up = int((~np.isnan(self.sst_host[0]).any(axis=1)).sum())
+            self.sst = NetworkBatch(self.Xs, self.Ys, self.Tfull, len(plan.sst_years), latlon=True, n_upper=n_up,
+                                    max_areas=max_areas)
+        self.P = plan.P
+        self.n_forecasts = plan.P
+        self.gp = GpBatch(max(1, self.P), max_pred=max_pred)
         # pinned staging buffers so every step pays a real host->device copy
-        self._pin = {name: torch.from_numpy(arr).pin_memory() for name, arr in self._host_inputs().items()}
+        self._pin = {name: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+                     for name, arr in self._host_inputs().items()}
 
     def _host_inputs(self):
-        d = {"sic": self.sic_host, "job_field": self.job_field_host, "job_T": self.job_T_host,
-             "rcrit": self.rcrit_host, "psar": self.psar_host, "prob": self.prob_host.view(np.uint8),
-             "y": self.y_host}
+        p = self.plan
+        d = {"sic": self.sic_host, "job_field": p.job_field, "job_T": p.job_T, "rcrit": p.rcrit,
+             "psar": self.psar_host, "prob": p.prob.view(np.uint8), "y": p.y}
         if self.use_sst:
-            d.update({"sst": self.sst_host, "sst_T": self.sst_T_host, "sst_rcrit": self.sst_rcrit_host,
-                      "lat": self.lat_host, "sst_field_idx": np.zeros(len(self.sst_years), dtype=np.int32)})
+            d.update({"sst": self.sst_host, "sst_T": p.sst_T, "sst_rcrit": p.sst_rcrit, "lat": self.lat_host,
+                      "sst_field_idx": np.zeros(len(p.sst_years), dtype=np.int32)})
         return d
 
     def h2d_bytes(self):
@@ -286,44 +340,52 @@ class RetrospectiveSweep:
         self.dev = {k: t.to("cuda", non_blocking=True) for k, t in self._pin.items()}
         return self.dev
 
-    def compute(self):
-        """Enqueue the whole hot path on the current stream (no host sync)."""
+    def compute(self, marks=None):
+        """Enqueue the whole hot path on the current stream (no host sync).  `marks`: optional list that receives
+        (stage name, torch.cuda.Event) pairs recorded after each stage, for per-kernel timing."""
         d = self.dev
-        self.sic.build(d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"], do_detrend=True)
-        if self.use_sst:
-            self.sst.build(d["sst"], d["sst_field_idx"], d["sst_T"], d["sst_rcrit"], d["lat"], do_detrend=True)
+
+        def mark(name):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
+        for tag, eng, args in (("sic", self.sic, (d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"])),
+                               ("sst", self.sst, (d.get("sst"), d.get("sst_field_idx"), d.get("sst_T"),
+                                                  d.get("sst_rcrit"), d.get("lat")))):
+            if eng is None:
+                continue
+            fields, job_field, job_T, rcrit, scale = args
+            eng.detrend_zscore(fields, job_field, job_T, do_detrend=True)
+            mark(tag + ".detrend_zscore")
+            eng.corr_tau(rcrit)
+            mark(tag + ".corr_tau")
+            eng.area_level()
+            mark(tag + ".area_level")
+            eng.intra_links(scale)
+            mark(tag + ".intra_links")
         self.gp.run(d["prob"], d["y"], self.sic, self.sst)
+        mark("gp")
 
     def kernel_launches(self):
+        """Kernels of libsie_b200 enqueued by one compute(): 11 per network batch + the GP kernel."""
         return 11 * (2 if self.use_sst else 1) + 1
 
     def download(self):
         """Device -> host read of the GP results (synchronises)."""
-        self.raw = self.gp.results()
+        self.raw = self.gp.results()[:self.P]
         return self.raw
 
     def run(self):
         self.upload()
         self.compute()
-        return self.assemble(self.download())
+        return self.plan.assemble(self.download())
 
-    def assemble(self, raw):
-        """-> {config: {region_fmean / _fvar / _fmean_rt: array(years)}} like the reference's GPR dict
-        (June1st_retro.py:284-290, values rounded to 3 d.p.), plus the un-rounded record under '_raw'."""
-        out = {}
-        for (ci, k, year), r in zip(self.prob_meta, raw):
-            cfg = self.cfgs[ci]
-            g = out.setdefault(cfg.name, {})
-            reg = cfg.regions[k]
-            for key in ("_fmean", "_fvar", "_fmean_rt"):
-                g.setdefault(reg + key, np.zeros(len(self.years)))
-            i = year - self.fmin
-            fmean = np.round(r["fmean"], 3)
-            row = year - (self.fmin - 1) - 1
-            slope, icpt = self.sie_trend[reg][row]
-            lineT = (np.arange(year - FIRST_YEAR + 1) * slope) + icpt
-            g[reg + "_fmean"][i] = fmean
-            g[reg + "_fvar"][i] = np.round(r["fvar"], 3)
-            g[reg + "_fmean_rt"][i] = np.round(fmean + lineT[-1], 3)
-        out["_raw"] = raw
-        return out
+    def check_status(self):
+        st = self.sic.status.cpu().numpy()
+        bad = np.nonzero(st == _lib.SIE_JOB_CAPACITY)[0]
+        if bad.size:
+            raise _lib.SieError(f"capacity exceeded in SIC jobs {bad.tolist()}")
+        return st

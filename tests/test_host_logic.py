@@ -1,0 +1,132 @@
+"""Host-side logic that needs no GPU: config table, year/row bookkeeping of the sweep, SIE tables, thresholds,
+task sharding (world_size 2 over gloo)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+from scipy import stats
+
+from oracle import sweep as osweep
+from seaiceextentforecasting_b200.config import CONFIGS, LS, NORTH_INITS, RULE_ALL, RULE_POS, RULE_POS_SIG, SS
+from seaiceextentforecasting_b200.engine import pad_T, r_crit_pearson, r_crit_ttest
+from seaiceextentforecasting_b200.forecast import GP_RESULT_DTYPE, SweepPlan, sie_detrend_tables
+
+
+def test_config_table_matches_reference_scripts():
+    c = CONFIGS
+    assert c["north_june"].ell == (LS[16], LS[14], LS[12]) and c["north_june"].sig == (SS[1], SS[4], SS[6])
+    assert c["north_june"].zscore and c["north_june"].use_sst and c["north_june"].rule == (RULE_POS,) * 3
+    assert c["north_july"].ell[2] == 3.125433e+10 and c["north_july"].sig[2] == 40221.26298973
+    assert c["north_august"].alpha == 0.08 and c["north_august"].rule == (RULE_ALL, RULE_POS_SIG, RULE_POS_SIG)
+    assert c["north_september"].alpha == 0.05 and c["north_september"].ell == (LS[8], LS[9], LS[3])
+    assert c["south_february"].sig == (SS[0], SS[11], SS[13])
+    assert c["south_january"].prev_year_network and c["south_january"].alpha == 0.08
+    assert c["south_december"].prev_year_network and c["south_december"].rule == (RULE_POS,) * 3
+
+
+def test_thresholds_equivalent_to_reference_tests():
+    rng = np.random.default_rng(0)
+    for T in (7, 12, 30, 42):
+        rc = r_crit_ttest(T, 0.01)
+        R = rng.uniform(0, 1, 4000)
+        df = T - 2
+        P = stats.t.sf(R * np.sqrt(df / (1 - R ** 2)), df)          # ComplexNetworks.py:43-45
+        assert np.array_equal(P < 0.01, R > rc)
+    for n in (6, 10, 20, 41):
+        for a in (0.05, 0.08):
+            rc = r_crit_pearson(n, a)
+            x = rng.standard_normal((300, n))
+            y = rng.standard_normal(n)
+            for row in x:
+                r, p = stats.pearsonr(y, row)
+                assert bool((r > 0) & (p / 2 < a)) == bool(r > 0 and r > rc)
+
+
+def test_pad_T_is_conflict_free_stride():
+    for T in range(3, 64):
+        Tp = pad_T(T)
+        assert Tp >= T and Tp % 8 == 4 and Tp - T < 8
+
+
+def test_sie_tables_match_oracle_linregress():
+    rng = np.random.default_rng(3)
+    sie = np.round(6 - 0.08 * np.arange(42) + 0.3 * rng.standard_normal(42), 3)
+    dt, tr = sie_detrend_tables(sie, 1985, 2020)
+    odt, otr = osweep.sie_tables(sie, 1985, 2020)
+    assert np.array_equal(dt, odt)                                   # rounded to 3 d.p. in both
+    np.testing.assert_allclose(tr, otr, rtol=1e-12, atol=1e-14)
+
+
+def _sie():
+    rng = np.random.default_rng(0)
+    return {r: np.round(rng.standard_normal(42), 3) for r in ("Pan-Arctic", "Beaufort", "Chukchi")}
+
+
+def test_north_sweep_plan_counts():
+    p = SweepPlan(NORTH_INITS, _sie(), 1985, 2020)
+    assert len(p.jobs) == 144 and len(p.sst_years) == 36 and p.P == 432
+    assert p.job_T.min() == 7 and p.job_T.max() == 42
+    for (ci, k, year), pr in zip(p.prob_meta, p.prob):
+        assert pr["n"] == year - 1979 and p.job_T[pr["job_sic"]] == pr["n"] + 1
+        assert (pr["job_sst"] >= 0) == p.cfgs[ci].use_sst
+
+
+def test_south_prev_year_plan():
+    sie = {r: v for r, v in zip(("Pan-Antarctic", "Ross", "Weddell"), _sie().values())}
+    p = SweepPlan(["south_january"], sie, 1985, 2020)
+    for (ci, k, year), pr in zip(p.prob_meta, p.prob):
+        assert pr["n"] == year - 1979 - 1                            # y drops 1979 (January1st_retro.py:175)
+        assert p.jobs[pr["job_sic"]] == (0, year - 1)                # previous year's network
+        assert p.job_T[pr["job_sic"]] == pr["n"] + 1
+
+
+def test_shards_partition_the_sweep():
+    full = SweepPlan(NORTH_INITS, _sie(), 1985, 2020)
+    for world in (2, 4, 8):
+        parts = [SweepPlan(NORTH_INITS, _sie(), 1985, 2020, rank=r, world=world) for r in range(world)]
+        metas = [m for p in parts for m in p.prob_meta]
+        assert sorted(metas) == sorted(full.prob_meta)
+        loads = [int((p.job_T.astype(np.int64) ** 2).sum()) for p in parts]
+        assert max(loads) <= 1.15 * min(loads)                       # balanced by window length
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    plan = SweepPlan(NORTH_INITS, _sie(), 2015, 2020, rank=rank, world=world)
+    raw = np.zeros(plan.P, dtype=GP_RESULT_DTYPE)
+    for i, (ci, k, year) in enumerate(plan.prob_meta):               # fake kernel output: encodes the problem id
+        raw["fmean"][i] = ci * 1000 + k * 100 + (year - 2000)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (plan.prob_meta, raw.tobytes()))
+    if rank == 0:
+        meta = [m for g in gathered for m in g[0]]
+        allraw = np.concatenate([np.frombuffer(g[1], dtype=GP_RESULT_DTYPE) for g in gathered])
+        out = plan.assemble(allraw, meta)
+        ok = True
+        for ci, cfg in enumerate(plan.cfgs):
+            for k, reg in enumerate(cfg.regions):
+                exp = np.array([ci * 1000 + k * 100 + (y - 2000) for y in plan.years], dtype=float)
+                ok &= np.array_equal(out[cfg.name][reg + "_raw_fmean"], exp)
+        q.put(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_assembles_full_sweep():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok

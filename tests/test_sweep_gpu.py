@@ -1,0 +1,96 @@
+"""GPU parity of the batched retrospective sweep (the bench workload) against the golden outputs of the unmodified
+reference scripts (tests/golden/sweep_*.npz) and against the oracle on a multi-init north sweep."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from seaiceextentforecasting_b200 import synthetic as syn
+from seaiceextentforecasting_b200.config import CONFIGS, NORTH_INITS
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SWEEPS = sorted(glob.glob(os.path.join(GOLD, "sweep_*.npz")))
+
+
+def unpack_V(g, suffix=""):
+    keys, lens, cells = g["V_keys" + suffix], g["V_lens" + suffix], g["V_cells" + suffix]
+    V, off = {}, 0
+    for k, ln in zip(keys, lens):
+        V[int(k)] = [[int(a), int(b)] for a, b in cells[off:off + ln]]
+        off += ln
+    return V
+
+
+def gp_tol(rec):
+    """1e-9 relative, widened by the documented 2^s amplification of expm's squaring phase."""
+    return max(1e-9, 64.0 * 2.0 ** int(rec["expm_s"]) * 2.0 ** -53)
+
+
+@pytest.mark.parametrize("path", SWEEPS, ids=[os.path.basename(p) for p in SWEEPS])
+def test_sweep_matches_reference_golden(lib_built, path):
+    from seaiceextentforecasting_b200.forecast import RetrospectiveSweep
+    g = np.load(path)
+    name = os.path.basename(path)[len("sweep_"):-len(".npz")]
+    cfg = CONFIGS[name]
+    fmin, fmax = int(g["fmin"]), int(g["fmax"])
+    sie = {r: g["sie"][i] for i, r in enumerate(cfg.regions)}
+    sw = RetrospectiveSweep([name], {name: g["sic"]}, sie, fmin, fmax, g["psar"],
+                            g["sst"] if cfg.use_sst else None, g["sst_lat"] if cfg.use_sst else None)
+    out = sw.run()
+    raw = sw.raw
+    assert (raw["info"] == 0).all()
+    # every network of the sweep: bit-exact area membership and order
+    for (st, V), (ci, ny) in zip(sw.sic.areas_to_host(), sw.plan.jobs):
+        assert st == 0
+        assert V == unpack_V(g, f"_{ny}"), ny
+    for k, reg in enumerate(cfg.regions):
+        for suf in ("_fmean", "_fvar", "_fmean_rt"):
+            ref = g["raw_" + reg + suf]
+            got = out[name][reg + "_raw" + suf]
+            for i, year in enumerate(sw.years):
+                rec = raw[sw.plan.prob_meta.index((0, k, year))]
+                scale = max(abs(ref[i]), 1e-2)
+                assert abs(got[i] - ref[i]) <= 50 * gp_tol(rec) * scale, (reg, suf, year, got[i], ref[i], rec)
+            # the reference's own output format: rounded to 3 d.p.
+            rnd = g["rnd_" + reg + suf]
+            assert np.max(np.abs(out[name][reg + suf] - rnd)) <= 1.0e-3 + 1e-12
+    sk = sw.plan.skill(out)[name]
+    assert np.all(np.abs(np.array(sk[0]) - g["skill_rt"]) <= 0.02)
+    assert np.all(np.abs(np.array(sk[1]) - g["skill_dt"]) <= 0.02)
+
+
+def test_multi_init_north_sweep_matches_oracle(lib_built):
+    """All four north inits + SST in one batch (the bench's structure at a size the oracle finishes in seconds)."""
+    from oracle import sweep as osweep
+    from seaiceextentforecasting_b200.forecast import RetrospectiveSweep
+    fmin, fmax = 1993, 1996
+    Tfull = fmax - 1979 + 1
+    sic, sie0 = {}, None
+    for i, name in enumerate(NORTH_INITS):
+        f, _ = syn.make_field(15, 15, Tfull, 300 + i, n_modes=50, noise=0.5, blob=(1.0, 2.5))
+        sic[name] = f
+        if sie0 is None:
+            sie0 = syn.make_sie(f, Tfull, 300)
+    sie = dict(zip(CONFIGS["north_june"].regions, sie0))
+    sst, _ = syn.make_field(8, 18, Tfull, 399, latlon=True, saturate=False, n_modes=20, noise=0.5, blob=(1.0, 2.5))
+    psar, lat = syn.make_psar(15, 15), syn.make_lat_grid(8, 18)
+    sw = RetrospectiveSweep(NORTH_INITS, sic, sie, fmin, fmax, psar, sst, lat)
+    out = sw.run()
+    cfgs = [CONFIGS[n] for n in NORTH_INITS]
+    try:
+        ora = osweep.retro_sweep(cfgs, sic, sie, fmin, fmax, psar, sst, lat)
+    except (ValueError, IndexError, np.linalg.LinAlgError) as e:      # the reference crashes on <2 predictors
+        pytest.skip(f"oracle/reference raises on this input: {e}")
+    for (st, V), (ci, ny) in zip(sw.sic.areas_to_host(), sw.plan.jobs):
+        assert V == ora[cfgs[ci].name]["V"][ny]
+    for ci, cfg in enumerate(cfgs):
+        for k, reg in enumerate(cfg.regions):
+            for i, year in enumerate(sw.years):
+                rec = sw.raw[sw.plan.prob_meta.index((ci, k, year))]
+                assert rec["info"] == 0
+                for suf in ("_fmean", "_fvar"):
+                    ref = ora[cfg.name][reg + suf][i]
+                    got = out[cfg.name][reg + "_raw" + suf][i]
+                    assert abs(got - ref) <= 50 * gp_tol(rec) * max(abs(ref), 1e-2), (cfg.name, reg, year, got, ref)

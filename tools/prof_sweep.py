@@ -1,0 +1,24 @@
+import sys, json
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+from seaiceextentforecasting_b200.config import NORTH_INITS
+from seaiceextentforecasting_b200.forecast import RetrospectiveSweep
+w=bench.make_workload(0)
+sw=RetrospectiveSweep(NORTH_INITS,w['sic'],w['sie'],bench.FMIN,bench.FMAX,w['psar'],w['sst'],w['lat'])
+out=sw.run(); out=sw.run()
+torch.cuda.synchronize()
+for tag,eng,T in (('sic',sw.sic,sw.plan.job_T),('sst',sw.sst,sw.plan.sst_T)):
+    wk=eng.area_work.cpu().numpy(); na=eng.n_areas.cpu().numpy(); nn=eng.n_nodes.cpu().numpy()
+    order=np.argsort(-(wk[:,1]+wk[:,2]))
+    print(tag,'job T N nA gathers step1_Mcyc step2_Mcyc steps rounds')
+    for b in list(order[:8])+list(order[-3:]):
+        print(tag,b,T[b],nn[b],na[b],wk[b,0],round(wk[b,1]/1e6,2),round(wk[b,2]/1e6,2),wk[b,3]>>32,wk[b,3]&0xffffffff)
+    print(tag,'sum step1 Mcyc',wk[:,1].sum()/1e6,'sum step2',wk[:,2].sum()/1e6)
+raw=sw.raw
+order=np.argsort(-raw['cycles_total'])
+print('gp: idx meta n npred m s info total_Mcyc expm_Mcyc')
+for i in list(order[:12])+list(order[-3:]):
+    print(i,sw.plan.prob_meta[i],sw.plan.prob[i]['n'],raw[i]['n_pred'],raw[i]['expm_m'],raw[i]['expm_s'],raw[i]['info'],round(raw[i]['cycles_total']/1e6,3),round(raw[i]['cycles_expm']/1e6,3))
+print('gp sum total Mcyc',raw['cycles_total'].sum()/1e6,'expm',raw['cycles_expm'].sum()/1e6, 'bad',[(i,sw.plan.prob_meta[i],raw[i]['info'],raw[i]['n_pred']) for i in np.nonzero(raw['info'])[0]])
+print('s hist',np.bincount(raw['expm_s']), 'npred max',raw['n_pred'].max(), 'mean', raw['n_pred'].mean())
