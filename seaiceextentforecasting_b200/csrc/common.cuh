@@ -37,50 +37,42 @@ __device__ __forceinline__ double sie_nan() { return __longlong_as_double(0x7ff8
 // sums, so the device evaluates them in exactly this order.
 //
 // `sie_pw_leaf8`: an aligned group of 8 lanes (lane j = accumulator j) sums one leaf (n <= 128) of a
-// sequence whose i-th element is get(i); NaN entries count as 0 and are tallied in `nan_cnt` (nanmean).
-// All 8 lanes return the same value.
+// sequence whose i-th element is get(i); NaN entries count as 0 and are tallied in `nan_cnt` (nanmean; the
+// per-lane tallies must be summed over the group by the caller).  All 8 lanes return the same value.
 // -------------------------------------------------------------------------------------------------
 template <typename Get>
 __device__ __forceinline__ double sie_pw_leaf8(Get get, int lo, int n, int j, unsigned gmask, int& nan_cnt) {
+  // All gathers of the leaf (<= 16 per lane + one tail element) are issued before the first add, so a leaf costs
+  // one memory round trip; the adds then run in numpy's order.
+  const int nfull = (n < 8) ? 0 : n - (n & 7);
+  const int ngrp = nfull >> 3;                       // <= 16 full groups of 8
+  const int ntail = n - nfull;                       // < 8 (or all of a short list)
+  double v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = (k < ngrp) ? get(lo + 8 * k + j) : 0.0;
+  double tv = (j < ntail) ? get(lo + nfull + j) : 0.0;
+  if (tv != tv) { tv = 0.0; ++nan_cnt; }
   double res;
-  if (n < 8) {
-    // every lane walks the short list itself (identical values in all lanes)
-    res = 0.0;
-    for (int i = 0; i < n; ++i) {
-      double v = get(lo + i);
-      if (v != v) { v = 0.0; if (j == 0) ++nan_cnt; }
-      res = __dadd_rn(res, v);
+  if (ngrp == 0) {
+    res = 0.0;                                       // n < 8: left-to-right from 0.0
+  } else {
+    double r = v[0];
+    if (r != r) { r = 0.0; ++nan_cnt; }
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+      if (k < ngrp) {
+        double x = v[k];
+        if (x != x) { x = 0.0; ++nan_cnt; }
+        r = __dadd_rn(r, x);
+      }
     }
-    return res;
+    // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) : xor-butterfly inside the 8-lane group (IEEE add commutes)
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+    res = r;
   }
-  const int nfull = n - (n & 7);
-  double r = get(lo + j);
-  if (r != r) { r = 0.0; ++nan_cnt; }
-  int i = 8;
-  // batches of 4 independent gathers keep several loads in flight per lane
-  for (; i + 24 < nfull; i += 32) {
-    double v0 = get(lo + i + j), v1 = get(lo + i + 8 + j), v2 = get(lo + i + 16 + j), v3 = get(lo + i + 24 + j);
-    if (v0 != v0) { v0 = 0.0; ++nan_cnt; }
-    if (v1 != v1) { v1 = 0.0; ++nan_cnt; }
-    if (v2 != v2) { v2 = 0.0; ++nan_cnt; }
-    if (v3 != v3) { v3 = 0.0; ++nan_cnt; }
-    r = __dadd_rn(r, v0); r = __dadd_rn(r, v1); r = __dadd_rn(r, v2); r = __dadd_rn(r, v3);
-  }
-  for (; i < nfull; i += 8) {
-    double v = get(lo + i + j);
-    if (v != v) { v = 0.0; ++nan_cnt; }
-    r = __dadd_rn(r, v);
-  }
-  // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) : xor-butterfly inside the 8-lane group (IEEE add commutes)
-  r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));
-  r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));
-  r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
-  res = r;
-  for (int t = nfull; t < n; ++t) {
-    double v = get(lo + t);
-    if (v != v) { v = 0.0; if (j == 0) ++nan_cnt; }
-    res = __dadd_rn(res, v);
-  }
+  for (int t = 0; t < ntail; ++t) res = __dadd_rn(res, __shfl_sync(gmask, tv, t, 8));   // tail, left to right
   return res;
 }
 

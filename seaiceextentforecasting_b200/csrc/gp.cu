@@ -35,16 +35,27 @@ __device__ const double kB13[14] = {64764752532480000., 32382376266240000., 7771
                                     129060195264000., 10559470521600., 670442572800., 33522128640., 1323241920.,
                                     40840800., 960960., 16380., 182., 1.};
 
+constexpr int KC = 16;            // GEMM k-chunk
+constexpr int LDA_S = 20;         // As[64][20]: row stride = 4 (mod 16) doubles -> conflict-free DMMA A fragments
+constexpr int LDB_S = 68;         // Bs[16][68]: same property for B fragments
+constexpr int PANEL = 16;         // LU panel width
+
 struct Smem {
-  double As[16][64 + 2];
-  double Bs[16][64 + 2];
-  double K[MAXN * LDS];     // kernel matrix / Cholesky factor
-  double W[MAXN * LDS];     // X Sigma~ X^T
-  double y[MAXN], ya[MAXN], alpha[MAXN], kxs[MAXN], v[MAXN], xs_tmp[MAXN];
+  double As[2][64 * LDA_S];
+  double Bs[2][KC * LDB_S];
+  union {
+    struct {
+      double K[MAXN * LDS];       // kernel matrix / Cholesky factor
+      double W[MAXN * LDS];       // X Sigma~ X^T
+    } gp;
+    double panel[2 * MAXN * LDS]; // LU panel (rows x PANEL), only live inside cta_lu_solve
+  } u;
+  double y[MAXN], ya[MAXN], alpha[MAXN], kxs[MAXN], v[MAXN];
   double red[GT / 32];
   int ired[GT / 32];
   int misc[8];
   double dmisc[8];
+  int piv[PANEL];
 };
 
 __device__ __forceinline__ double block_sum(double v, Smem& sm) {
@@ -70,66 +81,99 @@ __device__ __forceinline__ double block_max(double v, Smem& sm) {
   return r;
 }
 
-// C[m x n2] = A[m x k] * B[k x n2]; row-major, leading dimensions lda/ldb/ldc; C must not alias A or B.
-__device__ void cta_gemm(double* __restrict__ Cm, int ldc, const double* __restrict__ A, int lda,
-                         const double* __restrict__ Bm, int ldb, int m, int k, int n2, Smem& sm) {
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  for (int i0 = 0; i0 < m; i0 += 64) {
-    for (int j0 = 0; j0 < n2; j0 += 64) {
-      double acc[4][4];
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// C[m x n2] (op)= A[m x k] * B[k x n2]; row-major with leading dimensions; C must not alias A or B.
+//   mode 0: C = A*B      mode 1: C -= A*B
+// 64x64 output tiles, 8 warps in a 4x2 grid (16x32 per warp = 2x4 DMMA.8x8x4 blocks), k in chunks of 16.
+// The (tile, k-chunk) steps are flattened into one software pipeline: the global loads of step s+1 are issued into
+// registers before the tensor work of step s and parked in the other shared-memory buffer afterwards, so one
+// barrier per step suffices and L2 latency hides behind the MMAs even when k = 16 (the LU trailing updates).
+__device__ __noinline__ void cta_gemm(double* __restrict__ Cm, int ldc, const double* __restrict__ A, int lda,
+                         const double* __restrict__ Bm, int ldb, int m, int k, int n2, Smem& sm, int mode = 0) {
+  if (m <= 0 || n2 <= 0 || k <= 0) { __syncthreads(); return; }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = warp >> 1, wc = warp & 1;
+  const int tm = (m + 63) >> 6, tn = (n2 + 63) >> 6, kc = (k + KC - 1) / KC;
+  const int nsteps = tm * tn * kc;
+  // loader roles: A tile 64 x 16: thread -> (row = tid/4, 4 consecutive k); B tile 16 x 64: (kk = tid/16, 4 cols)
+  const int ar = tid >> 2, ak = (tid & 3) * 4;
+  const int bk = tid >> 4, bc = (tid & 15) * 4;
+  double ra[4], rb[4];
+  auto gload = [&](int step) {
+    const int t = step / kc, c = step - t * kc;
+    const int ti = t / tn, tj = t - ti * tn;
+    const int gr = ti * 64 + ar, gk = c * KC + ak;
+    const double* pa = A + (size_t)gr * lda + gk;
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+    for (int q = 0; q < 4; ++q) ra[q] = (gr < m && gk + q < k) ? pa[q] : 0.0;
+    const int gkb = c * KC + bk, gc = tj * 64 + bc;
+    const double* pb = Bm + (size_t)gkb * ldb + gc;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-      for (int k0 = 0; k0 < k; k0 += 16) {
-        {  // A tile 64 x 16 -> As[kk][row]
-          const int r = tid >> 2, kk = (tid & 3) * 4;
-          const int gr = i0 + r;
+    for (int q = 0; q < 4; ++q) rb[q] = (gkb < k && gc + q < n2) ? pb[q] : 0.0;
+  };
+  auto spark = [&](int bufi) {
+    double* as = sm.As[bufi] + ar * LDA_S + ak;
+    double* bs = sm.Bs[bufi] + bk * LDB_S + bc;
+    *reinterpret_cast<double2*>(as) = make_double2(ra[0], ra[1]);
+    *reinterpret_cast<double2*>(as + 2) = make_double2(ra[2], ra[3]);
+    *reinterpret_cast<double2*>(bs) = make_double2(rb[0], rb[1]);
+    *reinterpret_cast<double2*>(bs + 2) = make_double2(rb[2], rb[3]);
+  };
+  double acc[2][4][2];
+  gload(0);
+  spark(0);
+  __syncthreads();
+  for (int step = 0; step < nsteps; ++step) {
+    const int bufi = step & 1;
+    const int t = step / kc, c = step - t * kc;
+    if (step + 1 < nsteps) gload(step + 1);
+    if (c == 0) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int gk = k0 + kk + q;
-            sm.As[kk + q][r] = (gr < m && gk < k) ? A[(size_t)gr * lda + gk] : 0.0;
-          }
-        }
-        {  // B tile 16 x 64 -> Bs[kk][col]
-          const int kk = tid >> 4, c = (tid & 15) * 4;
-          const int gk = k0 + kk;
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int gc = j0 + c + q;
-            sm.Bs[kk][c + q] = (gk < k && gc < n2) ? Bm[(size_t)gk * ldb + gc] : 0.0;
-          }
-        }
-        __syncthreads();
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
+    }
+    const double* as = sm.As[bufi] + (wr * 16 + (lane >> 2)) * LDA_S + (lane & 3);
+    const double* bs = sm.Bs[bufi] + (lane & 3) * LDB_S + wc * 32 + (lane >> 2);
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-          double a[4], b[4];
+    for (int ks = 0; ks < KC / 4; ++ks) {
+      double af[2], bf[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { a[q] = sm.As[kk][ty * 4 + q]; b[q] = sm.Bs[kk][tx * 4 + q]; }
+      for (int i = 0; i < 2; ++i) af[i] = as[i * 8 * LDA_S + ks * 4];
 #pragma unroll
-          for (int p = 0; p < 4; ++p)
+      for (int jj = 0; jj < 4; ++jj) bf[jj] = bs[ks * 4 * LDB_S + jj * 8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[p][q] = fma(a[p], b[q], acc[p][q]);
-        }
-        __syncthreads();
-      }
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int gr = i0 + ty * 4 + p;
+        for (int jj = 0; jj < 4; ++jj) dmma884(acc[i][jj][0], acc[i][jj][1], af[i], bf[jj]);
+    }
+    if (c == kc - 1) {   // tile finished: write / update C straight from the accumulator fragments
+      const int ti = t / tn, tj = t - ti * tn;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int gr = ti * 64 + wr * 16 + i * 8 + (lane >> 2);
         if (gr >= m) continue;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int gc = j0 + tx * 4 + q;
-          if (gc < n2) Cm[(size_t)gr * ldc + gc] = acc[p][q];
+        for (int jj = 0; jj < 4; ++jj) {
+          const int gc = tj * 64 + wc * 32 + jj * 8 + 2 * (lane & 3);
+          double* pc = Cm + (size_t)gr * ldc + gc;
+          if (gc < n2) pc[0] = mode ? pc[0] - acc[i][jj][0] : acc[i][jj][0];
+          if (gc + 1 < n2) pc[1] = mode ? pc[1] - acc[i][jj][1] : acc[i][jj][1];
         }
       }
     }
+    if (step + 1 < nsteps) spark(bufi ^ 1);
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 // ||A||_1 = max column sum of |A| (Np x Np)
-__device__ double cta_norm1(const double* __restrict__ A, int ld, int np_, Smem& sm) {
+__device__ __noinline__ double cta_norm1(const double* __restrict__ A, int ld, int np_, Smem& sm) {
   double best = 0.0;
   for (int j = threadIdx.x; j < np_; j += GT) {
     double s = 0.0;
@@ -140,7 +184,7 @@ __device__ double cta_norm1(const double* __restrict__ A, int ld, int np_, Smem&
 }
 
 // exact || (scale*|A|)^p ||_1 by p transposed mat-vecs on the ones vector (non-negative matrix)
-__device__ double cta_absnorm_power(const double* __restrict__ A, int ld, int np_, double scale, int p,
+__device__ __noinline__ double cta_absnorm_power(const double* __restrict__ A, int ld, int np_, double scale, int p,
                                     double* __restrict__ v0, double* __restrict__ v1, Smem& sm) {
   for (int j = threadIdx.x; j < np_; j += GT) v0[j] = 1.0;
   __syncthreads();
@@ -170,7 +214,7 @@ __device__ __forceinline__ int ell_of(double t, double normA, int idx, int m) {
 }
 
 // dst = c0*I + c1*P1 + c2*P2 + c3*P3 (+ add) ; any pointer may be null
-__device__ void cta_lincomb(double* __restrict__ dst, int ld, int np_, double cI, const double* P1, double c1,
+__device__ __noinline__ void cta_lincomb(double* __restrict__ dst, int ld, int np_, double cI, const double* P1, double c1,
                             const double* P2, double c2, const double* P3, double c3, const double* add) {
   for (int idx = threadIdx.x; idx < np_ * np_; idx += GT) {
     const int i = idx / np_, jj = idx - i * np_;
@@ -185,67 +229,130 @@ __device__ void cta_lincomb(double* __restrict__ dst, int ld, int np_, double cI
   __syncthreads();
 }
 
-// Solve P X = Q in place (X overwrites Q) by Gaussian elimination with partial pivoting; P is destroyed.
-__device__ void cta_lu_solve(double* __restrict__ P, double* __restrict__ Q, int ld, int np_, Smem& sm) {
+// Solve P X = Q in place (X overwrites Q): right-looking blocked LU with partial pivoting (panel width 16, the
+// panel factored in shared memory, trailing updates of [P | Q] as rank-16 DMMA GEMMs), then a blocked back
+// substitution.  P is destroyed.  Same algorithm family as LAPACK dgesv (scipy's solve step inside expm).
+__device__ __noinline__ void cta_lu_solve(double* __restrict__ P, double* __restrict__ Q, int ld, int np_, Smem& sm) {
   const int tid = threadIdx.x;
-  for (int k = 0; k < np_; ++k) {
-    // pivot search
-    double bv = -1.0; int bi = k;
-    for (int i = k + tid; i < np_; i += GT) {
-      const double a = fabs(P[(size_t)i * ld + k]);
-      if (a > bv) { bv = a; bi = i; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  double* pan = sm.u.panel;                       // [rows][PANEL]
+  for (int k0 = 0; k0 < np_; k0 += PANEL) {
+    const int kb = min(PANEL, np_ - k0);
+    const int rows = np_ - k0;
+    for (int idx = tid; idx < rows * PANEL; idx += GT) {
+      const int r = idx / PANEL, c = idx - r * PANEL;
+      pan[idx] = (c < kb) ? P[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
     }
     __syncthreads();
-    if ((tid & 31) == 0) { sm.red[tid >> 5] = bv; sm.ired[tid >> 5] = bi; }
-    __syncthreads();
-    bv = sm.red[0]; bi = sm.ired[0];
-#pragma unroll
-    for (int w = 1; w < GT / 32; ++w)
-      if (sm.red[w] > bv || (sm.red[w] == bv && sm.ired[w] < bi)) { bv = sm.red[w]; bi = sm.ired[w]; }
-    if (bi != k) {
-      for (int jj = tid; jj < np_; jj += GT) {
-        if (jj >= k) { const double t = P[(size_t)k * ld + jj]; P[(size_t)k * ld + jj] = P[(size_t)bi * ld + jj]; P[(size_t)bi * ld + jj] = t; }
-        const double t2 = Q[(size_t)k * ld + jj]; Q[(size_t)k * ld + jj] = Q[(size_t)bi * ld + jj]; Q[(size_t)bi * ld + jj] = t2;
+    for (int c = 0; c < kb; ++c) {
+      double bv = -1.0; int bi = c;
+      for (int r = c + tid; r < rows; r += GT) {
+        const double a = fabs(pan[r * PANEL + c]);
+        if (a > bv) { bv = a; bi = r; }
       }
-    }
-    __syncthreads();
-    const double piv = P[(size_t)k * ld + k];
-    // eliminate rows below k: row i handled by a group of threads across columns
-    const int rows = np_ - k - 1;
-    const int cols = (np_ - k - 1) + np_;   // trailing columns of P plus all of Q
-    for (int idx = tid; idx < rows * cols; idx += GT) {
-      const int r = idx / cols, c = idx - r * cols;
-      const int i = k + 1 + r;
-      const double l = P[(size_t)i * ld + k] / piv;
-      if (c < np_ - k - 1) {
-        const int jj = k + 1 + c;
-        P[(size_t)i * ld + jj] = fma(-l, P[(size_t)k * ld + jj], P[(size_t)i * ld + jj]);
-      } else {
-        const int jj = c - (np_ - k - 1);
-        Q[(size_t)i * ld + jj] = fma(-l, Q[(size_t)k * ld + jj], Q[(size_t)i * ld + jj]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
+      if ((tid & 31) == 0) { sm.red[tid >> 5] = bv; sm.ired[tid >> 5] = bi; }
+      __syncthreads();
+      bv = sm.red[0]; bi = sm.ired[0];
+#pragma unroll
+      for (int w = 1; w < GT / 32; ++w)
+        if (sm.red[w] > bv || (sm.red[w] == bv && sm.ired[w] < bi)) { bv = sm.red[w]; bi = sm.ired[w]; }
+      if (tid == 0) sm.piv[c] = bi;
+      if (bi != c && tid < PANEL) {
+        const double t = pan[c * PANEL + tid]; pan[c * PANEL + tid] = pan[bi * PANEL + tid]; pan[bi * PANEL + tid] = t;
+      }
+      __syncthreads();
+      const double inv = 1.0 / pan[c * PANEL + c];
+      for (int r = c + 1 + tid; r < rows; r += GT) pan[r * PANEL + c] *= inv;
+      __syncthreads();
+      const int cw = kb - c - 1;
+      if (cw > 0) {
+        for (int idx = tid; idx < (rows - c - 1) * cw; idx += GT) {
+          const int r = c + 1 + idx / cw, c2 = c + 1 + idx % cw;
+          pan[r * PANEL + c2] = fma(-pan[r * PANEL + c], pan[c * PANEL + c2], pan[r * PANEL + c2]);
+        }
+      }
+      __syncthreads();
+    }
+    // panel back to global; row swaps + L11^-1 applied to the columns right of the panel and to all of Q
+    for (int idx = tid; idx < rows * kb; idx += GT) {
+      const int r = idx / kb, c = idx - r * kb;
+      P[(size_t)(k0 + r) * ld + k0 + c] = pan[r * PANEL + c];
+    }
+    const int rightw = np_ - k0 - kb;
+    for (int col = tid; col < rightw + np_; col += GT) {
+      double* base = (col < rightw) ? P + (k0 + kb + col) : Q + (col - rightw);
+      for (int c = 0; c < kb; ++c) {
+        const int pr = sm.piv[c];
+        if (pr != c) {
+          const double t = base[(size_t)(k0 + c) * ld]; base[(size_t)(k0 + c) * ld] = base[(size_t)(k0 + pr) * ld];
+          base[(size_t)(k0 + pr) * ld] = t;
+        }
+      }
+      double x[PANEL];
+#pragma unroll
+      for (int c = 0; c < PANEL; ++c) x[c] = (c < kb) ? base[(size_t)(k0 + c) * ld] : 0.0;
+#pragma unroll
+      for (int c = 1; c < PANEL; ++c) {
+        if (c < kb) {
+          double sacc = x[c];
+#pragma unroll
+          for (int d = 0; d < PANEL; ++d)
+            if (d < c) sacc = fma(-pan[c * PANEL + d], x[d], sacc);
+          x[c] = sacc;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < PANEL; ++c)
+        if (c < kb) base[(size_t)(k0 + c) * ld] = x[c];
     }
     __syncthreads();
-  }
-  // back substitution, one thread per right-hand-side column
-  for (int jj = tid; jj < np_; jj += GT) {
-    for (int i = np_ - 1; i >= 0; --i) {
-      double s = Q[(size_t)i * ld + jj];
-      for (int c = i + 1; c < np_; ++c) s = fma(-P[(size_t)i * ld + c], Q[(size_t)c * ld + jj], s);
-      Q[(size_t)i * ld + jj] = s / P[(size_t)i * ld + i];
+    const int below = np_ - k0 - kb;
+    if (below > 0) {
+      const double* L21 = P + (size_t)(k0 + kb) * ld + k0;
+      cta_gemm(P + (size_t)(k0 + kb) * ld + k0 + kb, ld, L21, ld, P + (size_t)k0 * ld + k0 + kb, ld, below, kb, rightw,
+               sm, 1);
+      cta_gemm(Q + (size_t)(k0 + kb) * ld, ld, L21, ld, Q + (size_t)k0 * ld, ld, below, kb, np_, sm, 1);
     }
   }
-  __syncthreads();
+  // back substitution U X = Y, block rows from the bottom
+  const int nblk = (np_ + PANEL - 1) / PANEL;
+  for (int b = nblk - 1; b >= 0; --b) {
+    const int k0 = b * PANEL, kb = min(PANEL, np_ - k0);
+    for (int idx = tid; idx < PANEL * PANEL; idx += GT) {
+      const int r = idx / PANEL, c = idx - r * PANEL;
+      pan[idx] = (r < kb && c < kb) ? P[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
+    }
+    __syncthreads();
+    for (int col = tid; col < np_; col += GT) {
+      double x[PANEL];
+#pragma unroll
+      for (int c = 0; c < PANEL; ++c) x[c] = (c < kb) ? Q[(size_t)(k0 + c) * ld + col] : 0.0;
+#pragma unroll
+      for (int c = PANEL - 1; c >= 0; --c) {
+        if (c < kb) {
+          double sacc = x[c];
+#pragma unroll
+          for (int d = 0; d < PANEL; ++d)
+            if (d > c && d < kb) sacc = fma(-pan[c * PANEL + d], x[d], sacc);
+          x[c] = sacc / pan[c * PANEL + c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < PANEL; ++c)
+        if (c < kb) Q[(size_t)(k0 + c) * ld + col] = x[c];
+    }
+    __syncthreads();
+    if (k0 > 0) cta_gemm(Q, ld, P + k0, ld, Q + (size_t)k0 * ld, ld, k0, kb, np_, sm, 1);
+  }
 }
 
 // expm(A) for the Np x Np matrix in buf[1]; buf[0..8] are Np x Np slabs (ld).  Returns pointer to result.
-__device__ double* cta_expm(double** buf, int ld, int np_, double* v0, double* v1, int* m_out, int* s_out,
+__device__ __noinline__ double* cta_expm(double** buf, int ld, int np_, double* v0, double* v1, int* m_out, int* s_out,
                             Smem& sm) {
   double* A = buf[1]; double* A2 = buf[2]; double* A4 = buf[3]; double* A6 = buf[4];
   double* B5 = buf[5]; double* B6 = buf[6]; double* B7 = buf[7]; double* B8 = buf[8];
@@ -338,7 +445,7 @@ __device__ double* cta_expm(double** buf, int ld, int np_, double* v0, double* v
 }
 
 // in-place lower Cholesky of the n x n matrix K (shared, ld LDS); returns 0 or the 1-based failing pivot
-__device__ int cta_cholesky(double* K, int n, Smem& sm) {
+__device__ __noinline__ int cta_cholesky(double* K, int n, Smem& sm) {
   const int tid = threadIdx.x;
   for (int k = 0; k < n; ++k) {
     const double d = K[k * LDS + k];
@@ -391,11 +498,12 @@ __device__ void cta_chol_solve(const double* L, int n, const double* b, double* 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(GT, 1)
+__global__ void __launch_bounds__(GT, 2)
 k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __restrict__ y_all,
               const double* __restrict__ anom_sic, const int32_t* __restrict__ n_areas_sic, int ma_sic, int ts_sic,
               const double* __restrict__ anom_sst, const int32_t* __restrict__ n_areas_sst, int ma_sst, int ts_sst,
-              int max_pred, SieGpResult* __restrict__ out, unsigned char* __restrict__ scratch, size_t per_cta) {
+              int max_pred, SieGpResult* __restrict__ out, unsigned char* __restrict__ scratch, size_t per_cta,
+              const int32_t* __restrict__ order, int* __restrict__ queue) {
   extern __shared__ __align__(16) unsigned char smraw[];
   Smem& sm = *reinterpret_cast<Smem*>(smraw);
   const int tid = threadIdx.x;
@@ -412,7 +520,14 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
   double* Gg = colm + ld;                                              // [MAXN*LDS] gradient scratch
   int* sel = reinterpret_cast<int*>(Gg + MAXN * LDS);                  // [ld] selected series (sign in bit 30)
 
-  for (int p = blockIdx.x; p < P; p += gridDim.x) {
+  // dynamic work queue over problems pre-ordered by expected cost (largest first)
+  while (true) {
+    __syncthreads();
+    if (tid == 0) sm.misc[7] = atomicAdd(queue, 1);
+    __syncthreads();
+    const int qi = sm.misc[7];
+    if (qi >= P) break;
+    const int p = order ? order[qi] : qi;
     const SieGpProblem pr = prob[p];
     const int n = pr.n;
     SieGpResult res;
@@ -540,18 +655,18 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
       const int i = idx / n, jj = idx - i * n;
       double sacc = 0.0;
       for (int c = 0; c < np_; ++c) sacc = fma(XE[(size_t)i * ld + c], Xg[(size_t)jj * ld + c], sacc);
-      sm.W[i * LDS + jj] = sacc;
+      sm.u.gp.W[i * LDS + jj] = sacc;
     }
     __syncthreads();
     // ---- L~ = chol(W + sig I); A~ ; sigma_f = y^T A~ / n  (:265-267)
     for (int idx = tid; idx < n * n; idx += GT) {
       const int i = idx / n, jj = idx - i * n;
-      sm.K[i * LDS + jj] = sm.W[i * LDS + jj] + ((i == jj) ? pr.sig : 0.0);
+      sm.u.gp.K[i * LDS + jj] = sm.u.gp.W[i * LDS + jj] + ((i == jj) ? pr.sig : 0.0);
     }
     __syncthreads();
-    int info = cta_cholesky(sm.K, n, sm);
+    int info = cta_cholesky(sm.u.gp.K, n, sm);
     if (info) { if (tid == 0) { res.info = info; out[p] = res; } continue; }
-    cta_chol_solve(sm.K, n, sm.y, sm.ya, sm.v);
+    cta_chol_solve(sm.u.gp.K, n, sm.y, sm.ya, sm.v);
     double sf = 0.0;
     for (int t = 0; t < n; ++t) sf = fma(sm.y[t], sm.ya[t], sf);
     sf /= (double)n;
@@ -561,12 +676,12 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
     // ---- L = chol(sf*W + sn I); alpha (:269-271)
     for (int idx = tid; idx < n * n; idx += GT) {
       const int i = idx / n, jj = idx - i * n;
-      sm.K[i * LDS + jj] = sf * sm.W[i * LDS + jj] + ((i == jj) ? sn : 0.0);
+      sm.u.gp.K[i * LDS + jj] = sf * sm.u.gp.W[i * LDS + jj] + ((i == jj) ? sn : 0.0);
     }
     __syncthreads();
-    info = cta_cholesky(sm.K, n, sm);
+    info = cta_cholesky(sm.u.gp.K, n, sm);
     if (info) { if (tid == 0) { res.info = info; out[p] = res; } continue; }
-    cta_chol_solve(sm.K, n, sm.y, sm.alpha, sm.v);
+    cta_chol_solve(sm.u.gp.K, n, sm.y, sm.alpha, sm.v);
     // ---- predictive mean / variance (:272-277)
     for (int i = tid; i < n; i += GT) {
       double sacc = 0.0;
@@ -583,13 +698,13 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
     }
     const double kss = sf * block_sum(kss_part, sm) + sn;
     if (tid < 32) {
-      warp_fwd_solve(sm.K, n, sm.kxs, sm.v, tid);          // v = L^-1 KXXs
+      warp_fwd_solve(sm.u.gp.K, n, sm.kxs, sm.v, tid);          // v = L^-1 KXXs
       double vv = 0.0, fm = 0.0, ya = 0.0, ld_sum = 0.0;
       for (int i = tid; i < n; i += 32) {
         vv = fma(sm.v[i], sm.v[i], vv);
         fm = fma(sm.kxs[i], sm.alpha[i], fm);
         ya = fma(sm.y[i], sm.alpha[i], ya);
-        ld_sum += log(sm.K[i * LDS + i]);
+        ld_sum += log(sm.u.gp.K[i * LDS + i]);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -620,7 +735,7 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
             for (int c = 0; c < np_; ++c) sacc = fma(XM[(size_t)i * ld + c], Xg[(size_t)jj * ld + c], sacc);
             val = sf * sacc + ((i == jj) ? sn : 0.0);
           } else {
-            val = sf * sm.W[i * LDS + jj] + ((i == jj) ? sf : 0.0);
+            val = sf * sm.u.gp.W[i * LDS + jj] + ((i == jj) ? sf : 0.0);
           }
           Gg[i * LDS + jj] = val;
         }
@@ -638,13 +753,13 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
           const int jj = tid;
           for (int i = 0; i < n; ++i) {
             double sacc = Gg[i * LDS + jj];
-            for (int c = 0; c < i; ++c) sacc = fma(-sm.K[i * LDS + c], col[c], sacc);
-            col[i] = sacc / sm.K[i * LDS + i];
+            for (int c = 0; c < i; ++c) sacc = fma(-sm.u.gp.K[i * LDS + c], col[c], sacc);
+            col[i] = sacc / sm.u.gp.K[i * LDS + i];
           }
           for (int i = n - 1; i >= jj; --i) {
             double sacc = col[i];
-            for (int c = i + 1; c < n; ++c) sacc = fma(-sm.K[c * LDS + i], col[c], sacc);
-            col[i] = sacc / sm.K[i * LDS + i];
+            for (int c = i + 1; c < n; ++c) sacc = fma(-sm.u.gp.K[c * LDS + i], col[c], sacc);
+            col[i] = sacc / sm.u.gp.K[i * LDS + i];
           }
           tr = col[jj];
         }
@@ -658,11 +773,40 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
   }
 }
 
+// Orders problems by descending candidate-predictor count (a proxy for Np^3 expm cost) with a one-CTA counting
+// sort and resets the work-queue counter, so the biggest problems start first (LPT) on the persistent grid.
+constexpr int ORDER_BUCKETS = 2048;
+__global__ void __launch_bounds__(1024) k_gp_order(const SieGpProblem* __restrict__ prob, int P,
+                                                  const int32_t* __restrict__ n_areas_sic,
+                                                  const int32_t* __restrict__ n_areas_sst, int32_t* __restrict__ order,
+                                                  int* __restrict__ queue) {
+  __shared__ int hist[ORDER_BUCKETS];
+  for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  auto bucket = [&](int p) {
+    const SieGpProblem pr = prob[p];
+    int na = n_areas_sic[pr.job_sic] + ((pr.job_sst >= 0 && n_areas_sst) ? n_areas_sst[pr.job_sst] : 0);
+    if (pr.rule == 2) na = na / 2;                     // significance-filtered problems select fewer series
+    na = max(0, min(na, ORDER_BUCKETS - 1));
+    return ORDER_BUCKETS - 1 - na;                     // descending cost
+  };
+  for (int p = threadIdx.x; p < P; p += blockDim.x) atomicAdd(&hist[bucket(p)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < ORDER_BUCKETS; ++i) { const int c = hist[i]; hist[i] = acc; acc += c; }
+    *queue = 0;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < P; p += blockDim.x) order[atomicAdd(&hist[bucket(p)], 1)] = p;
+}
+
 __host__ size_t gp_per_cta_bytes(int max_pred) {
   size_t d = (size_t)9 * max_pred * max_pred + (size_t)3 * MAXN * max_pred + (size_t)3 * max_pred + (size_t)MAXN * LDS;
   size_t bytes = d * sizeof(double) + (size_t)max_pred * sizeof(int);
   return (bytes + 255) / 256 * 256;
 }
+__host__ size_t gp_header_bytes(int P) { return ((size_t)256 + (size_t)P * sizeof(int32_t) + 255) / 256 * 256; }
 int gp_grid(int P) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) {
@@ -671,7 +815,7 @@ int gp_grid(int P) {
   } else {
     (void)cudaGetLastError();
   }
-  const int g = 2 * sms;     // shared memory (~86 KB) allows two CTAs per SM
+  const int g = 2 * sms;     // shared memory (~106 KB) and 128 registers/thread allow two CTAs per SM
   return P < g ? P : g;
 }
 
@@ -679,7 +823,8 @@ int gp_grid(int P) {
 
 extern "C" size_t sie_gp_scratch_bytes(int P, int max_pred, int max_n) {
   (void)max_n;
-  return (size_t)gp_grid(P > 0 ? P : 1) * gp_per_cta_bytes(max_pred);
+  if (P < 1) P = 1;
+  return gp_header_bytes(P) + (size_t)gp_grid(P) * gp_per_cta_bytes(max_pred);
 }
 
 extern "C" int sie_gp_forecast(const SieGpProblem* prob, int P, const double* y_all, const double* anom_sic,
@@ -690,14 +835,22 @@ extern "C" int sie_gp_forecast(const SieGpProblem* prob, int P, const double* y_
   SIE_CHECK_ARG(prob && y_all && anom_sic && n_areas_sic && out && scratch, "null pointer");
   SIE_CHECK_ARG(P > 0 && max_pred > 0 && (max_pred % 4) == 0, "P>0 and max_pred a positive multiple of 4");
   const size_t per = gp_per_cta_bytes(max_pred);
+  const size_t head = gp_header_bytes(P);
+  SIE_CHECK_ARG(scratch_bytes >= head + per, "scratch too small");
+  SIE_CHECK_ARG(max_pred <= 2 * MAXN * LDS / PANEL, "max_pred above the LU panel capacity (520)");
   int grid = gp_grid(P);
-  if ((size_t)grid * per > scratch_bytes) grid = (int)(scratch_bytes / per);
+  if (head + (size_t)grid * per > scratch_bytes) grid = (int)((scratch_bytes - head) / per);
   SIE_CHECK_ARG(grid >= 1, "scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* queue = reinterpret_cast<int*>(scratch);
+  int32_t* order = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+  k_gp_order<<<1, 1024, 0, st>>>(prob, P, n_areas_sic, n_areas_sst, order, queue);
+  SIE_CHECK_LAUNCH();
   const size_t smem = sizeof(Smem);
   cudaFuncSetAttribute(k_gp_forecast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_gp_forecast<<<grid, GT, smem, (cudaStream_t)stream>>>(prob, P, y_all, anom_sic, n_areas_sic, max_areas_sic,
-                                                         Tstride_sic, anom_sst, n_areas_sst, max_areas_sst,
-                                                         Tstride_sst, max_pred, out, (unsigned char*)scratch, per);
+  k_gp_forecast<<<grid, GT, smem, st>>>(prob, P, y_all, anom_sic, n_areas_sic, max_areas_sic, Tstride_sic, anom_sst,
+                                        n_areas_sst, max_areas_sst, Tstride_sst, max_pred, out,
+                                        (unsigned char*)scratch + head, per, order, queue);
   SIE_CHECK_LAUNCH();
   return SIE_OK;
 }

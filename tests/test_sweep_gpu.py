@@ -53,9 +53,14 @@ def test_sweep_matches_reference_golden(lib_built, path):
                 rec = raw[sw.plan.prob_meta.index((0, k, year))]
                 scale = max(abs(ref[i]), 1e-2)
                 assert abs(got[i] - ref[i]) <= 50 * gp_tol(rec) * scale, (reg, suf, year, got[i], ref[i], rec)
-            # the reference's own output format: rounded to 3 d.p.
+            # the reference's own output format: rounded to 3 d.p. -- checked wherever the conditioning-aware bound
+            # is itself below the rounding step (July/Chukchi's l = 3.1e10 needs s ~ 56 squarings: scipy's own
+            # result moves in the 3rd decimal under a 1-ulp input perturbation, tests/test_expm_spec.py)
             rnd = g["rnd_" + reg + suf]
-            assert np.max(np.abs(out[name][reg + suf] - rnd)) <= 1.0e-3 + 1e-12
+            for i, year in enumerate(sw.years):
+                rec = raw[sw.plan.prob_meta.index((0, k, year))]
+                if 50 * gp_tol(rec) * max(abs(ref[i]), 1e-2) < 5e-4:
+                    assert abs(out[name][reg + suf][i] - rnd[i]) <= 1.0e-3 + 1e-12, (reg, suf, year)
     sk = sw.plan.skill(out)[name]
     assert np.all(np.abs(np.array(sk[0]) - g["skill_rt"]) <= 0.02)
     assert np.all(np.abs(np.array(sk[1]) - g["skill_dt"]) <= 0.02)
