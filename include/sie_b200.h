@@ -39,6 +39,8 @@ extern "C" {
 #define SIE_JOB_FEW_AREAS 2     /* ComplexNetworks.py:212/:278 would raise ValueError (<2 areas) */
 #define SIE_JOB_CAPACITY 3      /* more areas / nodes than the caller-provided capacity */
 
+#define SIE_AREA_WORK 16        /* uint64 profiling counters per job written by sie_area_level */
+
 int sie_abi_version(void);
 const char* sie_last_error(void);
 /* device facts used by the host layer for launch sizing; returns 0 on success */
@@ -102,8 +104,11 @@ int sie_corr_stencil(const double* R, const int32_t* node_cell, const int32_t* c
  * status     [B]  SIE_JOB_* (areas are still written when status == SIE_JOB_FEW_AREAS, like the
  *            reference leaves V populated when it raises at :278)
  * scratch    at least sie_area_level_scratch_bytes(B, X*Y) bytes
- * work       [B][4] or NULL: per job {correlations consumed (the algorithmic gather count, 8 B each),
- *            SM cycles in step 1, SM cycles in step 2, (growth steps << 32) | merge rounds}
+ * work       [B][SIE_AREA_WORK] or NULL: per job {0: correlations consumed (the algorithmic gather count, 8 B
+ *            each), 1: SM cycles in step 1, 2: SM cycles in step 2, 3: (growth steps << 32) | merge rounds,
+ *            4..14: SM cycles per phase (step 1: seed search, evaluate+argmax, frontier update, gathers;
+ *            step 2: select/materialise, neighbour discovery, neighbour lists, row means, statistic,
+ *            merge/finalise; 14 unused), 15: growth steps that took the re-summing path}
  */
 int sie_area_level(const double* R, const double* stencil, const int32_t* node_cell,
                    const int32_t* cell_node, const int32_t* n_nodes, const double* tau,

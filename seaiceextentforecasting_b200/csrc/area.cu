@@ -9,21 +9,35 @@
 // reference when fed the same R.  Candidate order (direction-major, then position in the area list,
 // duplicates kept) only matters for ties; it is carried as a per-cell key instead of materialising the
 // reference's candidate list.  Integer state lives in shared memory (global scratch for big grids).
-// Latency/gather bound: no roofline fraction is claimed for this kernel; see DESIGN.md.
+//
+// Latency engineering (the kernel is bound by its chain of dependent steps, not by bandwidth):
+//  * step 1 keeps, per frontier cell, numpy's 8 accumulators + the <8-element tail of its correlation list in
+//    shared memory.  While the area has <= 128 cells (one pairwise leaf) adding a cell appends ONE correlation per
+//    frontier cell (one gather, one L2 round trip per growth step) and the mean is re-assembled from the
+//    accumulators in numpy's order, bit-identical to summing the whole list again.  Larger areas fall back to
+//    re-summing gathered lists.
+//  * step 2 keeps a dense list-order copy D[p][q] = R[best_p][best_q] of the current largest area, extended when
+//    a neighbour is merged, so the O(n^2) "mean of row means" statistic of every hypothetical merge streams
+//    contiguous rows instead of re-gathering the best x best block for every candidate and round.
+// No roofline fraction is claimed for this kernel; see DESIGN.md.
 #include "common.cuh"
 
 namespace {
 
 constexpr int NT = 512;
 constexpr int NG = NT / 8;          // 8-lane groups per CTA
+constexpr int FCAP = NT;           // frontier slots with incremental state: one thread per slot
+constexpr int DCAP_MAX = 1024;     // rows/cols of the dense best-area sub-matrix
+constexpr int MAXCH = 32;          // neighbour areas evaluated per chunk of a merge round
 constexpr uint32_t NOKEY = 0xffffffffu;
 constexpr unsigned long long NOKEY64 = ~0ull;
 
 struct AreaScratch {   // per-job global scratch (byte offsets computed on host and device the same way)
   int32_t* s1_cells;   // [C] step-1 member cells, area after area
-  int32_t* ibuf;       // [5*C] fallback for the shared-memory integer arrays
+  int32_t* ibuf;       // [6*C] fallback for the shared-memory integer arrays
   int32_t* nbuf;       // [C] neighbour-area node lists (step 2)
   double* rowmean;     // [RM] row means of hypothetical areas
+  double* dmat;        // [dcap*dcap] dense list-order copy of R restricted to the current best area (step 2)
   int32_t* a_start;    // [MA] per step-1 area (segment)
   int32_t* a_len;      // [MA]
   int32_t* seg_next;   // [MA]
@@ -38,12 +52,14 @@ struct AreaScratch {   // per-job global scratch (byte offsets computed on host 
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline size_t rm_cap(int C) { return (size_t)4 * C + 1024; }
+__host__ __device__ inline int d_cap(int C) { return C < DCAP_MAX ? C : DCAP_MAX; }
 __host__ __device__ inline size_t scratch_per_job(int C, int MA) {
   size_t s = 0;
   s += align_up(sizeof(int32_t) * (size_t)C, 256);          // s1_cells
-  s += align_up(sizeof(int32_t) * (size_t)5 * C, 256);      // ibuf
+  s += align_up(sizeof(int32_t) * (size_t)6 * C, 256);      // ibuf
   s += align_up(sizeof(int32_t) * (size_t)C, 256);          // nbuf
   s += align_up(sizeof(double) * rm_cap(C), 256);           // rowmean
+  s += align_up(sizeof(double) * (size_t)d_cap(C) * d_cap(C), 256);   // dmat
   s += 8 * align_up(sizeof(int32_t) * (size_t)(MA + 1), 256);
   s += 2 * align_up(sizeof(double) * (size_t)MA, 256);
   return s;
@@ -52,9 +68,10 @@ __device__ inline AreaScratch carve(unsigned char* p, int C, int MA) {
   AreaScratch s;
   auto take = [&](size_t bytes) { unsigned char* r = p; p += align_up(bytes, 256); return r; };
   s.s1_cells = (int32_t*)take(sizeof(int32_t) * (size_t)C);
-  s.ibuf = (int32_t*)take(sizeof(int32_t) * (size_t)5 * C);
+  s.ibuf = (int32_t*)take(sizeof(int32_t) * (size_t)6 * C);
   s.nbuf = (int32_t*)take(sizeof(int32_t) * (size_t)C);
   s.rowmean = (double*)take(sizeof(double) * rm_cap(C));
+  s.dmat = (double*)take(sizeof(double) * (size_t)d_cap(C) * d_cap(C));
   s.a_start = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
   s.a_len = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
   s.seg_next = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
@@ -68,36 +85,46 @@ __device__ inline AreaScratch carve(unsigned char* p, int C, int MA) {
   return s;
 }
 
-struct Best {   // argmax record: larger mean wins, ties -> smaller key (earlier in the reference's list)
-  double mean;
-  unsigned long long key;
-  int idx;
+// Argmax record, compared branch-free as a 128-bit unsigned number: `hi` is an order-preserving image of the
+// mean (0 = no candidate), `lo` the tie-break priority (larger wins: the bitwise complement of the reference's
+// candidate-list position, so the earliest candidate wins ties) with the candidate index in its low bits.
+struct Pick {
+  unsigned long long hi, lo;
 };
-__device__ __forceinline__ bool better(const Best& a, const Best& b) {   // is a better than b
-  if (a.idx < 0) return false;
-  if (b.idx < 0) return true;
-  return a.mean > b.mean || (a.mean == b.mean && a.key < b.key);
+__device__ __forceinline__ unsigned long long ord_of(double x) {      // monotone map double -> u64, never 0
+  x = __dadd_rn(x, 0.0);                                               // -0.0 -> +0.0 (they compare equal)
+  const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
-__device__ __forceinline__ Best shfl_best(const Best& v, int o) {
-  Best r;
-  r.mean = __shfl_xor_sync(0xffffffffu, v.mean, o);
-  r.key = __shfl_xor_sync(0xffffffffu, v.key, o);
-  r.idx = __shfl_xor_sync(0xffffffffu, v.idx, o);
+__device__ __forceinline__ double ord_to_double(unsigned long long o) {
+  const unsigned long long u = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
+  return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ Pick pick_max(const Pick& a, const Pick& b) {
+  const bool tb = (b.hi > a.hi) || (b.hi == a.hi && b.lo > a.lo);
+  Pick r;
+  r.hi = tb ? b.hi : a.hi;
+  r.lo = tb ? b.lo : a.lo;
   return r;
 }
+__device__ __forceinline__ Pick pick_none() { Pick r; r.hi = 0ull; r.lo = 0ull; return r; }
 // CTA-wide argmax; every thread returns the same winner.  `slots` is shared scratch of NT/32 records.
-__device__ __forceinline__ Best block_best(Best v, Best* slots) {
+// `SyncBefore = false` is for callers that already placed a barrier between the previous call's reads and this one.
+template <bool SyncBefore = true>
+__device__ __forceinline__ Pick block_pick(Pick v, Pick* slots) {
 #pragma unroll
-  for (int o = 8; o < 32; o <<= 1) {   // lanes inside an 8-group already agree
-    Best w = shfl_best(v, o);
-    if (better(w, v)) v = w;
+  for (int o = 1; o < 32; o <<= 1) {
+    Pick w;
+    w.hi = __shfl_xor_sync(0xffffffffu, v.hi, o);
+    w.lo = __shfl_xor_sync(0xffffffffu, v.lo, o);
+    v = pick_max(v, w);
   }
-  __syncthreads();                     // slots may still be read from the previous call
+  if (SyncBefore) __syncthreads();     // slots may still be read from the previous call
   if ((threadIdx.x & 31) == 0) slots[threadIdx.x >> 5] = v;
   __syncthreads();
-  Best r = slots[0];
-  for (int w = 1; w < NT / 32; ++w)
-    if (better(slots[w], r)) r = slots[w];
+  Pick r = slots[0];
+#pragma unroll
+  for (int w = 1; w < NT / 32; ++w) r = pick_max(r, slots[w]);
   return r;
 }
 
@@ -112,9 +139,20 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
              unsigned char* __restrict__ scratch_all, size_t scratch_stride, int use_smem,
              unsigned long long* __restrict__ work_all) {
   extern __shared__ __align__(16) int32_t smem_i[];
-  __shared__ Best slots[NT / 32];
+  __shared__ Pick slots[NT / 32];
   __shared__ int sh_i[8];
+  __shared__ int sh_koff[MAXCH + 1], sh_uoff[MAXCH + 1];
   __shared__ unsigned long long sh_work;
+  __shared__ unsigned long long ph[12];   // per-phase SM cycles (thread 0's view), reported through work[4..15]
+  long long tick_last = 0;
+#define TICK(i)                                                        \
+  do {                                                                 \
+    if (tid == 0) {                                                    \
+      const long long t__ = clock64();                                 \
+      ph[i] += (unsigned long long)(t__ - tick_last);                  \
+      tick_last = t__;                                                 \
+    }                                                                  \
+  } while (0)
   unsigned long long wk = 0;   // correlations consumed (algorithmic gathers), tallied by lane 0 of each group
 
   const int b = blockIdx.x;
@@ -126,22 +164,32 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   const double tau = tau_all[b];
   const double* R = Rall + (size_t)b * ldn * ldn;
   const double* sten = stencil_all + (size_t)b * ldn * 4;
-  const int32_t* cnode = cell_node_all + (size_t)b * C;
+  const int32_t* cnode_g = cell_node_all + (size_t)b * C;
   int32_t* out_cells = area_cells_all + (size_t)b * C;
   int32_t* out_start = area_start_all + (size_t)b * (MA + 1);
   int32_t* out_key = area_key_all + (size_t)b * MA;
   int32_t* out_label = label_all + (size_t)b * C;
 
   AreaScratch S = carve(scratch_all + (size_t)b * scratch_stride, C, MA);
-  int32_t* ib = use_smem ? smem_i : S.ibuf;
+  // dynamic shared memory: [frontier-slot state: facc 8*FCAP f64 | ftail 8*FCAP f64 | fnan FCAP i32][6*C i32]
+  double* facc = reinterpret_cast<double*>(smem_i);     // [8][FCAP] numpy accumulator j of slot s at j*FCAP+s
+  double* ftail = facc + 8 * FCAP;                       // [8][FCAP] tail element t of slot s at t*FCAP+s
+  int32_t* fnan = reinterpret_cast<int32_t*>(ftail + 8 * FCAP);   // [FCAP] NaN entries seen by slot s
+  int32_t* ib = use_smem ? fnan + FCAP : S.ibuf;
   int32_t* lab = ib;                      // [C] area key of each cell, -1 = unassigned
   uint32_t* fkey = (uint32_t*)(ib + C);   // [C] frontier key (step 1)
   int32_t* flist = ib + 2 * C;            // [C] frontier cells (step 1)
   int32_t* hn = ib + 3 * C;               // [C] node list of the current area (step 1) / best area (step 2)
   int32_t* hc = ib + 4 * C;               // [C] cell list of the best area (step 2)
+  int32_t* cnl = ib + 5 * C;              // [C] local copy of cell -> node
+  int32_t* knl = (use_smem >= 2) ? ib + 6 * C : S.nbuf;   // [C] node lists of the neighbour areas (step 2)
+  const int32_t* cnode = cnl;
+  const int dcap = d_cap(C);
+  double* D = S.dmat;
 
-  for (int c = tid; c < C; c += NT) { lab[c] = -1; fkey[c] = NOKEY; out_label[c] = -1; }
-  if (tid == 0) { n_areas_all[b] = 0; out_start[0] = 0; sh_work = 0ull; if (work_all) work_all[4 * b] = 0ull; }
+  for (int c = tid; c < C; c += NT) { lab[c] = -1; fkey[c] = NOKEY; out_label[c] = -1; cnl[c] = cnode_g[c]; }
+  if (tid < 12) ph[tid] = 0ull;
+  if (tid == 0) { n_areas_all[b] = 0; out_start[0] = 0; sh_work = 0ull; if (work_all) work_all[SIE_AREA_WORK * b] = 0ull; }
   __syncthreads();
   if (first_nan_cell[b] < 0) {            // :50-51 IndexError in the reference
     if (tid == 0) status_all[b] = SIE_JOB_NO_NAN_CELL;
@@ -149,9 +197,96 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   }
   if (status_all[b] == SIE_JOB_CAPACITY) return;   // K1 already flagged this job
 
+  // ---- step-1 helpers --------------------------------------------------------------------------------
+  // gen_area_neighbours :80-94 for one member cell `cc` at list position `p` (no lat-lon wrap here): warp 0,
+  // lane d < 4 = direction.  New frontier cells are appended at flist[cnt..]; returns the new count.
+  auto frontier_add = [&](int cc, int p, int cnt) -> int {
+    bool isnew = false;
+    int f = -1;
+    if (lane < 4) {
+      const int d = lane;
+      const int ci = cc / Y, cj = cc - ci * Y;
+      const int a = ci + (d == 0 ? -1 : (d == 1 ? 1 : 0));
+      const int q = cj + (d == 2 ? -1 : (d == 3 ? 1 : 0));
+      if (a >= 0 && a < X && q >= 0 && q < Y) {
+        f = a * Y + q;
+        const int fn = cnode[f];
+        if (lab[f] >= 0 || fn < 0 || fn >= N) f = -1;
+      }
+      if (f >= 0) {
+        const uint32_t key = ((uint32_t)d << 28) | (uint32_t)p;
+        const uint32_t old = fkey[f];
+        isnew = (old == NOKEY);
+        if (key < old) fkey[f] = key;
+      }
+    }
+    const unsigned mnew = __ballot_sync(0xffffffffu, isnew);
+    if (isnew) flist[cnt + __popc(mnew & ((1u << lane) - 1u))] = f;
+    __syncwarp();
+    return cnt + __popc(mnew);
+  };
+  // numpy pairwise state of slot s (its frontier cell vs the first n <= 128 member cells): 8-lane group, lane j
+  // builds accumulator j = a[j] + a[8+j] + ... over the full groups of 8 and fetches tail element j.
+  auto init_slot = [&](int s, int n) {
+    const double* row = R + (size_t)cnode[flist[s]] * ldn;
+    const int ngrp = n >> 3, nt = n & 7;
+    double v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = (q < ngrp) ? __ldg(row + hn[8 * q + j]) : 0.0;
+    double tv = (j < nt) ? __ldg(row + hn[8 * ngrp + j]) : 0.0;
+    int nanc = 0;
+    if (tv != tv) { tv = 0.0; ++nanc; }
+    double r = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      if (q < ngrp) {
+        double x = v[q];
+        if (x != x) { x = 0.0; ++nanc; }
+        r = (q == 0) ? x : __dadd_rn(r, x);
+      }
+    }
+    facc[j * FCAP + s] = r;
+    ftail[j * FCAP + s] = tv;
+    nanc += __shfl_xor_sync(gmask, nanc, 1);
+    nanc += __shfl_xor_sync(gmask, nanc, 2);
+    nanc += __shfl_xor_sync(gmask, nanc, 4);
+    if (j == 0) fnan[s] = nanc;
+  };
+  // append element index n_old (value v) to slot s
+  auto fold_slot = [&](int s, double v, int n_old) {
+    if (v != v) { v = 0.0; fnan[s] += 1; }
+    const int t = n_old & 7;
+    if (t == 7) {                         // a group of 8 is complete: it joins the accumulators
+      if (n_old == 7) {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) facc[q * FCAP + s] = ftail[q * FCAP + s];
+        facc[7 * FCAP + s] = v;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) facc[q * FCAP + s] = __dadd_rn(facc[q * FCAP + s], ftail[q * FCAP + s]);
+        facc[7 * FCAP + s] = __dadd_rn(facc[7 * FCAP + s], v);
+      }
+    } else {
+      ftail[t * FCAP + s] = v;
+    }
+  };
+  // np.nanmean of slot s's list of n <= 128 correlations, in numpy's pairwise order
+  auto eval_slot = [&](int s, int n) -> double {
+    const int nt = n & 7;
+    double res = 0.0;
+    if (n >= 8) {
+      const double a0 = facc[s], a1 = facc[FCAP + s], a2 = facc[2 * FCAP + s], a3 = facc[3 * FCAP + s];
+      const double a4 = facc[4 * FCAP + s], a5 = facc[5 * FCAP + s], a6 = facc[6 * FCAP + s], a7 = facc[7 * FCAP + s];
+      res = __dadd_rn(__dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3)), __dadd_rn(__dadd_rn(a4, a5), __dadd_rn(a6, a7)));
+    }
+    for (int t = 0; t < nt; ++t) res = __dadd_rn(res, ftail[t * FCAP + s]);
+    return res / (double)(n - fnan[s]);
+  };
+
   // =============================================================== step 1 (:154-196)
   const long long clk0 = clock64();
-  unsigned long long n_steps = 0, n_rounds = 0;
+  tick_last = clk0;
+  unsigned long long n_steps = 0, n_rounds = 0, n_slow = 0;
   int nA = 0;        // areas created so far (uniform across the CTA)
   int base = 0;      // cells assigned so far
   bool overflow = false;
@@ -178,20 +313,12 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         if (!(mx > tau)) dir = -1;
       }
     }
-    Best cand;
-    cand.idx = (dir >= 0) ? c : -1;
-    cand.mean = 0.0;
-    cand.key = (unsigned long long)(unsigned)c;        // earliest cell wins
-    // lanes of an 8-group hold different cells here: reduce inside the group first
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      Best w = shfl_best(cand, o);
-      if (better(w, cand)) cand = w;
-    }
-    // carry the chosen direction alongside (recomputed by the owner thread below)
-    Best win = block_best(cand, slots);
-    if (win.idx < 0) { c0 += NT; continue; }
-    const int seed = win.idx;
+    Pick cand = pick_none();
+    if (dir >= 0) { cand.hi = 1ull; cand.lo = ~(unsigned long long)(unsigned)c; }   // earliest cell wins
+    const Pick win = block_pick(cand, slots);
+    TICK(0);                              // seed search
+    if (win.hi == 0ull) { c0 += NT; continue; }
+    const int seed = (int)(unsigned)(~win.lo);
     if (tid == seed - c0) sh_i[0] = dir;
     __syncthreads();
     const int sd = sh_i[0];
@@ -209,75 +336,97 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
     const int k = nA;
     int n = 2, nf = 0;
     __syncthreads();
-    if (tid == 0) {
-      lab[seed] = k; lab[nbr] = k;
-      hn[0] = cnode[seed]; hn[1] = cnode[nbr];
-      S.s1_cells[base] = seed; S.s1_cells[base + 1] = nbr;
-      int cnt = 0;
-      for (int p = 0; p < 2; ++p) {
-        const int cc = (p == 0) ? seed : nbr;
-        const int ci = cc / Y, cj = cc - ci * Y;
-        for (int d = 0; d < 4; ++d) {     // gen_area_neighbours :80-94 (no wrap here)
-          const int a = ci + (d == 0 ? -1 : (d == 1 ? 1 : 0));
-          const int q = cj + (d == 2 ? -1 : (d == 3 ? 1 : 0));
-          if (a < 0 || a >= X || q < 0 || q >= Y) continue;
-          const int f = a * Y + q;
-          const int fn = cnode[f];
-          if (lab[f] >= 0 || fn < 0 || fn >= N) continue;
-          const uint32_t key = ((uint32_t)d << 28) | (uint32_t)p;
-          if (fkey[f] == NOKEY) flist[cnt++] = f;
-          if (key < fkey[f]) fkey[f] = key;
-        }
+    if (tid < 32) {                       // warp 0 owns the integer bookkeeping
+      if (lane == 0) {
+        lab[seed] = k; lab[nbr] = k;
+        hn[0] = cnode[seed]; hn[1] = cnode[nbr];
+        S.s1_cells[base] = seed; S.s1_cells[base + 1] = nbr;
       }
-      sh_i[1] = cnt;
+      __syncwarp();
+      int cnt = frontier_add(seed, 0, 0);
+      cnt = frontier_add(nbr, 1, cnt);
+      if (lane == 0) sh_i[1] = cnt;
     }
     __syncthreads();
     nf = sh_i[1];
+    bool fast = (nf <= FCAP);             // incremental accumulators valid (uniform across the CTA)
+    if (fast) {
+      for (int s = g; s < nf; s += NG) init_slot(s, n);
+      __syncthreads();
+    }
+    TICK(3);                              // area creation + first slot states
     while (nf > 0) {
-      Best loc; loc.idx = -1; loc.mean = 0.0; loc.key = 0;
-      for (int q = g; q < nf; q += NG) {
-        const int f = flist[q];
-        const double* row = R + (size_t)cnode[f] * ldn;
-        int nanc = 0;
-        const double sum = sie_pw_sum8([&](int i) { return __ldg(row + hn[i]); }, n, j, gmask, nanc);
-        if (j == 0) wk += (unsigned long long)n;
-        nanc += __shfl_xor_sync(gmask, nanc, 1);
-        nanc += __shfl_xor_sync(gmask, nanc, 2);
-        nanc += __shfl_xor_sync(gmask, nanc, 4);
-        const double mean = sum / (double)(n - nanc);   // np.nanmean: NaN -> 0, divide by the non-NaN count
-        if (mean == mean) {
-          Best cur; cur.mean = mean; cur.key = fkey[f]; cur.idx = q;
-          if (better(cur, loc)) loc = cur;
+      Pick loc = pick_none();
+      if (!fast) ++n_slow;
+      if (fast) {
+        TICK(11);
+        if (tid < nf) {
+          const double mean = eval_slot(tid, n);
+          if (mean == mean) { loc.hi = ord_of(mean); loc.lo = ((unsigned long long)(~fkey[flist[tid]]) << 32) | (unsigned)tid; }
+        }
+        if (tid == 0) wk += (unsigned long long)n * (unsigned long long)nf;
+      } else {
+        for (int q = g; q < nf; q += NG) {
+          const int f = flist[q];
+          const double* row = R + (size_t)cnode[f] * ldn;
+          int nanc = 0;
+          const double sum = sie_pw_sum8([&](int i) { return __ldg(row + hn[i]); }, n, j, gmask, nanc);
+          if (j == 0) wk += (unsigned long long)n;
+          nanc += __shfl_xor_sync(gmask, nanc, 1);
+          nanc += __shfl_xor_sync(gmask, nanc, 2);
+          nanc += __shfl_xor_sync(gmask, nanc, 4);
+          const double mean = sum / (double)(n - nanc);   // np.nanmean: NaN -> 0, divide by the non-NaN count
+          if (mean == mean) {
+            Pick cur; cur.hi = ord_of(mean); cur.lo = ((unsigned long long)(~fkey[f]) << 32) | (unsigned)q;
+            loc = pick_max(loc, cur);
+          }
         }
       }
-      const Best win2 = block_best(loc, slots);
-      if (win2.idx < 0 || !(win2.mean > tau)) break;     // :134 (nanmax of all-NaN is NaN -> stop)
-      if (tid == 0) {
-        const int m = flist[win2.idx];
-        lab[m] = k;
-        hn[n] = cnode[m];
-        S.s1_cells[base + n] = m;
-        fkey[m] = NOKEY;
-        int cnt = nf - 1;
-        flist[win2.idx] = flist[cnt];
-        const int ci = m / Y, cj = m - ci * Y;
-        for (int d = 0; d < 4; ++d) {
-          const int a = ci + (d == 0 ? -1 : (d == 1 ? 1 : 0));
-          const int q = cj + (d == 2 ? -1 : (d == 3 ? 1 : 0));
-          if (a < 0 || a >= X || q < 0 || q >= Y) continue;
-          const int f = a * Y + q;
-          const int fn = cnode[f];
-          if (lab[f] >= 0 || fn < 0 || fn >= N) continue;
-          const uint32_t key = ((uint32_t)d << 28) | (uint32_t)n;
-          if (fkey[f] == NOKEY) flist[cnt++] = f;
-          if (key < fkey[f]) fkey[f] = key;
+      TICK(10);                           // evaluate
+      const Pick win2 = block_pick<false>(loc, slots);   // the barrier closing the previous step already ran
+      TICK(1);                            // argmax
+      if (win2.hi == 0ull || !(ord_to_double(win2.hi) > tau)) break;   // :134 (nanmax of all-NaN is NaN -> stop)
+      const int widx = (int)(unsigned)(win2.lo & 0xffffffffull);
+      const int last = nf - 1;
+      if (tid < 32) {
+        const int m = flist[widx];
+        __syncwarp();
+        if (lane == 0) {
+          lab[m] = k;
+          hn[n] = cnode[m];
+          S.s1_cells[base + n] = m;
+          fkey[m] = NOKEY;
+          flist[widx] = flist[last];
+          sh_i[4] = m;
         }
-        sh_i[1] = cnt;
+        __syncwarp();
+        const int cnt = frontier_add(m, n, last);
+        if (lane == 0) sh_i[1] = cnt;
+      } else if (tid < 64 && fast && widx != last) {   // slot state follows the cell moved into the hole
+        const int l2 = lane;
+        if (l2 < 8) facc[l2 * FCAP + widx] = facc[l2 * FCAP + last];
+        else if (l2 < 16) ftail[(l2 - 8) * FCAP + widx] = ftail[(l2 - 8) * FCAP + last];
+        else if (l2 == 16) fnan[widx] = fnan[last];
       }
       __syncthreads();
+      TICK(2);                            // frontier update
       nf = sh_i[1];
+      if (fast) {
+        if (n + 1 > 128 || nf > FCAP) {
+          fast = false;                   // beyond one pairwise leaf: re-sum gathered lists from here on
+        } else {
+          const int mnode = hn[n];
+          // new frontier cells (slots last..nf-1): build their state over the n+1 member cells; use the highest
+          // groups, which rarely own an old slot as well
+          for (int s = last + (NG - 1 - g); s < nf; s += NG) init_slot(s, n + 1);
+          // old frontier cells: append the correlation with the new member
+          if (tid < last) fold_slot(tid, __ldg(R + (size_t)cnode[flist[tid]] * ldn + mnode), n);
+        }
+      }
       ++n;
       ++n_steps;
+      __syncthreads();
+      TICK(3);                            // one gather per frontier cell + new-slot states
     }
     __syncthreads();
     for (int q = tid; q < nf; q += NT) fkey[flist[q]] = NOKEY;
@@ -296,27 +445,49 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
 
   // =============================================================== step 2 (:200-265)
   const long long clk1 = clock64();
+  tick_last = clk1;
   // `taken` is now "belongs to a finalised area"; lab[] keeps tracking the current owner key.
   int cur_best = -1, nb = 0;     // best area whose lists are materialised in hn/hc
   const size_t RM = rm_cap(C);
+  bool d_ok = false;             // dense block valid for the first nb member cells
+  // Dense list-order copy of R restricted to the best area, stored by diagonals: element (p, q), q > p, lives at
+  // D[(q-p-1)*dcap + p], so thread p walking its row p+1, p+2, ... reads addresses consecutive with its
+  // neighbours' (coalesced) in the row-mean pass.  extend_D adds the pairs with from <= q < to.
+  auto extend_D = [&](int from, int to) {
+    d_ok = (to <= dcap) && (from == 0 || d_ok);
+    if (!d_ok) return;
+    for (int i0 = 0; i0 < to - 1; i0 += 8) {            // 8 diagonals per pass: 8 gathers in flight per thread
+      const int plo = max(0, from - 8 - i0);
+      for (int pp = plo + tid; pp < to - 1 - i0; pp += NT) {
+        const double* row = R + (size_t)hn[pp] * ldn;
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int q = pp + 1 + i0 + u;
+          v[u] = (q < to && q >= from) ? __ldg(row + hn[q]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int q = pp + 1 + i0 + u;
+          if (q < to && q >= from) D[(size_t)(i0 + u) * dcap + pp] = v[u];
+        }
+      }
+    }
+    __syncthreads();
+  };
   while (true) {
     // --- largest not-yet-final area, first key on ties (:207-212)
-    Best loc; loc.idx = -1; loc.mean = 0.0; loc.key = 0;
+    Pick loc = pick_none();
     for (int k = tid; k < nA; k += NT) {
       const int sz = S.size[k];
       if (sz > 0) {             // still a key of V
-        Best cur; cur.mean = S.fin[k] ? 0.0 : (double)sz; cur.key = (unsigned long long)k; cur.idx = k;
-        if (better(cur, loc)) loc = cur;
+        Pick cur; cur.hi = ord_of(S.fin[k] ? 0.0 : (double)sz); cur.lo = ~(unsigned long long)(unsigned)k;
+        loc = pick_max(loc, cur);
       }
     }
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      Best w = shfl_best(loc, o);
-      if (better(w, loc)) loc = w;
-    }
-    const Best bw = block_best(loc, slots);
-    if (bw.idx < 0 || bw.mean == 0.0) break;   // no areas at all (ValueError at :212) or all finalised
-    const int best = bw.idx;
+    const Pick bw = block_pick(loc, slots);
+    if (bw.hi == 0ull || ord_to_double(bw.hi) == 0.0) break;   // no areas at all (:212) or all finalised
+    const int best = (int)(unsigned)(~bw.lo);
     ++n_rounds;
     if (best != cur_best) {                    // materialise V[best] in list order
       int off = 0;
@@ -327,9 +498,12 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
       }
       nb = off;
       cur_best = best;
+      __syncthreads();
+      extend_D(0, nb);
     }
     if (tid == 0) sh_i[2] = 0;
     __syncthreads();
+    TICK(4);                              // pick the largest area, materialise its lists / dense block
     // --- neighbouring areas in discovery order (:217-223): key = (position of X in V[best], dict key, dir)
     for (int p = tid; p < nb; p += NT) {
       const int cc = hc[p];
@@ -352,112 +526,115 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
     }
     __syncthreads();
     const int nn = sh_i[2];
+    TICK(5);                              // neighbour discovery
     // --- hypothetical merges (:224-253), neighbours processed in chunks that fit the row-mean buffer
     int q0 = 0;
     while (q0 < nn) {
       // chunk = neighbours q0..q1-1 ; every thread computes the same partition
       int q1 = q0;
       size_t rows = 0, cells = 0;
-      while (q1 < nn) {
+      while (q1 < nn && q1 - q0 < MAXCH) {
         const int sz = S.size[S.nlist[q1]];
         if (q1 > q0 && (rows + nb + sz > RM || cells + sz > (size_t)C)) break;
         rows += nb + sz; cells += sz; ++q1;
       }
-      // materialise the neighbours' node lists
+      // materialise the neighbours' node lists; sh_koff = node-list offsets, sh_uoff = row-unit offsets
       if (tid == 0) {
-        int off = 0;
-        for (int q = q0; q < q1; ++q) { S.noff[q] = off; off += S.size[S.nlist[q]]; }
-        S.noff[q1] = off;
+        int off = 0, uo = 0;
+        for (int q = q0; q < q1; ++q) {
+          const int sz = S.size[S.nlist[q]];
+          sh_koff[q - q0] = off; sh_uoff[q - q0] = uo;
+          off += sz; uo += nb + sz;
+        }
+        sh_koff[q1 - q0] = off; sh_uoff[q1 - q0] = uo;
       }
       __syncthreads();
       for (int q = q0; q < q1; ++q) {
-        int off = S.noff[q];
+        int off = sh_koff[q - q0];
         for (int s = S.nlist[q]; s >= 0; s = S.seg_next[s]) {
           const int st = S.a_start[s], ln = S.a_len[s];
-          for (int i = tid; i < ln; i += NT) S.nbuf[off + i] = cnode[S.s1_cells[st + i]];
+          for (int i = tid; i < ln; i += NT) knl[off + i] = cnode[S.s1_cells[st + i]];
           off += ln;
         }
       }
       __syncthreads();
-      // row means r_p = nanmean(R[hyp_p, hyp_q], q > p); unit u = (neighbour q, row p)
+      TICK(6);                            // neighbour node lists
+      // row means r_p = nanmean(R[hyp_p, hyp_q], q > p): ONE THREAD per (neighbour, row), consecutive threads on
+      // consecutive rows so the best x best part streams coalesced from the diagonal-major dense block
       {
-        size_t ubase = 0;
-        for (int q = q0; q < q1; ++q) {
-          const int nk = S.noff[q + 1] - S.noff[q];
+        const int nch = q1 - q0;
+        const int total = sh_uoff[nch];
+        for (int u = tid; u < total; u += NT) {
+          int qc = 0;
+          while (u >= sh_uoff[qc + 1]) ++qc;
+          const int p = u - sh_uoff[qc];
+          const int nk = sh_koff[qc + 1] - sh_koff[qc];
           const int n = nb + nk;
-          const int32_t* kn = S.nbuf + S.noff[q];
-          double* rm = S.rowmean + ubase;
-          for (int p = g; p < n; p += NG) {
-            const int len = n - 1 - p;
-            const int rownode = (p < nb) ? hn[p] : kn[p - nb];
-            const double* row = R + (size_t)rownode * ldn;
-            int nanc = 0;
-            double sum = 0.0;
-            if (len > 0) {
-              if (j == 0) wk += (unsigned long long)len;
-              sum = sie_pw_sum8(
-                  [&](int i) { const int t = p + 1 + i; return __ldg(row + ((t < nb) ? hn[t] : kn[t - nb])); },
-                  len, j, gmask, nanc);
-              nanc += __shfl_xor_sync(gmask, nanc, 1);
-              nanc += __shfl_xor_sync(gmask, nanc, 2);
-              nanc += __shfl_xor_sync(gmask, nanc, 4);
+          const int32_t* kn = knl + sh_koff[qc];
+          const int len = n - 1 - p;
+          int nanc = 0;
+          double sum = 0.0;
+          if (len > 0) {
+            wk += (unsigned long long)len;
+            if (p < nb) {
+              const double* row = R + (size_t)hn[p] * ldn;
+              const int nbb = nb - 1 - p;              // elements of the row inside the best area
+              if (d_ok) {
+                const double* dcol = D + p;
+                sum = sie_pw_sum_thread(
+                    [&](int i) { return (i < nbb) ? dcol[(size_t)i * dcap] : __ldg(row + kn[i - nbb]); }, len, nanc);
+              } else {
+                sum = sie_pw_sum_thread(
+                    [&](int i) { return __ldg(row + ((i < nbb) ? hn[p + 1 + i] : kn[i - nbb])); }, len, nanc);
+              }
+            } else {
+              const double* row = R + (size_t)kn[p - nb] * ldn;
+              const int32_t* kq = kn + (p - nb) + 1;
+              sum = sie_pw_sum_thread([&](int i) { return __ldg(row + kq[i]); }, len, nanc);
             }
-            if (j == 0) rm[p] = (len - nanc > 0) ? sum / (double)(len - nanc) : sie_nan();   // nanmean([]) = nan
           }
-          ubase += n;
+          S.rowmean[u] = (len - nanc > 0) ? sum / (double)(len - nanc) : sie_nan();   // nanmean([]) = nan
         }
       }
       __syncthreads();
+      TICK(7);                            // row means of the hypothetical areas
       // stat_k = nanmean(r_0..r_{n-1})  (:253) -- one 8-lane group per neighbour
-      {
-        size_t ubase = 0;
-        for (int q = q0; q < q1; ++q) {
-          const int n = nb + S.noff[q + 1] - S.noff[q];
-          if (g == (q - q0) % NG) {
-            const double* rm = S.rowmean + ubase;
-            int nanc = 0;
-            const double sum = sie_pw_sum8([&](int i) { return rm[i]; }, n, j, gmask, nanc);
-            nanc += __shfl_xor_sync(gmask, nanc, 1);
-            nanc += __shfl_xor_sync(gmask, nanc, 2);
-            nanc += __shfl_xor_sync(gmask, nanc, 4);
-            if (j == 0) S.stat[S.nlist[q]] = (n - nanc > 0) ? sum / (double)(n - nanc) : sie_nan();
-          }
-          ubase += n;
-        }
+      for (int q = q0 + g; q < q1; q += NG) {
+        const int n = sh_uoff[q - q0 + 1] - sh_uoff[q - q0];
+        const double* rm = S.rowmean + sh_uoff[q - q0];
+        int nanc = 0;
+        const double sum = sie_pw_sum8([&](int i) { return rm[i]; }, n, j, gmask, nanc);
+        nanc += __shfl_xor_sync(gmask, nanc, 1);
+        nanc += __shfl_xor_sync(gmask, nanc, 2);
+        nanc += __shfl_xor_sync(gmask, nanc, 4);
+        if (j == 0) S.stat[S.nlist[q]] = (n - nanc > 0) ? sum / (double)(n - nanc) : sie_nan();
       }
       __syncthreads();
+      TICK(8);                            // statistic per neighbour
       q0 = q1;
     }
     // --- max(Anei_Rs.items(), key=itemgetter(1)) (:255): first in discovery order wins ties; a NaN in
     //     first position is never displaced (list comparison semantics)
-    Best loc2; loc2.idx = -1; loc2.mean = 0.0; loc2.key = 0;
-    unsigned long long first_key = NOKEY64; int first_idx = -1;
+    Pick loc2 = pick_none(), f1 = pick_none();
     for (int q = tid; q < nn; q += NT) {
       const int kk = S.nlist[q];
       const double st = S.stat[kk];
       const unsigned long long ok = S.okey[kk];
-      if (ok < first_key) { first_key = ok; first_idx = kk; }
+      Pick c1; c1.hi = 1ull; c1.lo = ~ok;               // first discovered neighbour = smallest discovery key
+      f1 = pick_max(f1, c1);
       if (st == st) {
-        Best cur; cur.mean = st; cur.key = ok; cur.idx = kk;
-        if (better(cur, loc2)) loc2 = cur;
+        Pick cur; cur.hi = ord_of(st); cur.lo = ~ok;
+        loc2 = pick_max(loc2, cur);
       }
     }
-    // first discovered neighbour (min okey) -- reuse the argmax machinery with mean fixed
-    Best f1; f1.idx = first_idx; f1.mean = 0.0; f1.key = first_key;
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      Best w = shfl_best(loc2, o);
-      if (better(w, loc2)) loc2 = w;
-      Best w1 = shfl_best(f1, o);
-      if (better(w1, f1)) f1 = w1;
-    }
-    const Best firstn = block_best(f1, slots);
-    const Best win = block_best(loc2, slots);
+    const Pick firstn = block_pick(f1, slots);
+    const Pick win = block_pick(loc2, slots);
     bool merge = false;
     int kk = -1;
-    if (nn > 0 && win.idx >= 0) {
-      const double first_stat = S.stat[firstn.idx];
-      if (first_stat == first_stat && win.mean > tau) { merge = true; kk = win.idx; }
+    if (nn > 0 && win.hi != 0ull) {
+      const int first_idx = (int)((~firstn.lo >> 2) & 0x3fffffffull);
+      const double first_stat = S.stat[first_idx];
+      if (first_stat == first_stat && ord_to_double(win.hi) > tau) { merge = true; kk = (int)((~win.lo >> 2) & 0x3fffffffull); }
     }
     __syncthreads();
     // reset discovery keys
@@ -480,11 +657,13 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         S.size[best] += S.size[kk];
         S.size[kk] = 0;
       }
+      extend_D(nb, off);
       nb = off;
     } else {
       if (tid == 0) S.fin[best] = 1;           // :262-265 all cells of V[best] become unavailable
     }
     __syncthreads();
+    TICK(9);                              // winner, merge / finalise, dense block extension
   }
 
   // =============================================================== output in dict order (ascending key)
@@ -492,10 +671,12 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   __syncthreads();
   if (tid == 0 && work_all) {
     const long long clk2 = clock64();
-    work_all[4 * b] = sh_work;                                  // correlations consumed
-    work_all[4 * b + 1] = (unsigned long long)(clk1 - clk0);    // SM cycles in step 1
-    work_all[4 * b + 2] = (unsigned long long)(clk2 - clk1);    // SM cycles in step 2
-    work_all[4 * b + 3] = (n_steps << 32) | n_rounds;           // growth steps, merge rounds
+    work_all[SIE_AREA_WORK * b] = sh_work;                                  // correlations consumed
+    work_all[SIE_AREA_WORK * b + 1] = (unsigned long long)(clk1 - clk0);    // SM cycles in step 1
+    work_all[SIE_AREA_WORK * b + 2] = (unsigned long long)(clk2 - clk1);    // SM cycles in step 2
+    work_all[SIE_AREA_WORK * b + 3] = (n_steps << 32) | n_rounds;           // growth steps, merge rounds
+    for (int i = 0; i < 11; ++i) work_all[SIE_AREA_WORK * b + 4 + i] = ph[i];
+    work_all[SIE_AREA_WORK * b + 15] = ph[11];
   }
   if (tid == 0) {
     int cnt = 0, off = 0;
@@ -553,9 +734,12 @@ extern "C" int sie_area_level(const double* R, const double* stencil, const int3
   int dev = 0, max_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  size_t smem = sizeof(int32_t) * (size_t)5 * C;
-  int use_smem = (smem + 4096 <= (size_t)max_optin) ? 1 : 0;
-  if (!use_smem) smem = 0;
+  const size_t slot_bytes = sizeof(double) * 16 * FCAP + sizeof(int32_t) * FCAP;
+  // shared-memory tiers: 2 = all seven integer arrays, 1 = six (neighbour lists stay in global), 0 = slot state only
+  size_t smem = slot_bytes + sizeof(int32_t) * (size_t)7 * C;
+  int use_smem = 2;
+  if (smem + 4096 > (size_t)max_optin) { smem = slot_bytes + sizeof(int32_t) * (size_t)6 * C; use_smem = 1; }
+  if (smem + 4096 > (size_t)max_optin) { smem = slot_bytes; use_smem = 0; }
   cudaFuncSetAttribute(k_area_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_area_level<<<B, NT, smem, (cudaStream_t)stream>>>(
       R, stencil, node_cell, cell_node, n_nodes, tau, first_nan_cell, X, Y, ldn, latlon, max_areas, area_cells,

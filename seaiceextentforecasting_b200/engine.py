@@ -106,7 +106,7 @@ class NetworkBatch:
         self.label = torch.empty((B_, C_), dtype=i32, device=dev)
         self.area_scratch_bytes = int(self.lib.sie_area_level_scratch_bytes(B_, C_))
         self.area_scratch = torch.empty((self.area_scratch_bytes + 7) // 8, dtype=f64, device=dev)
-        self.area_work = torch.zeros((B_, 4), dtype=torch.int64, device=dev)
+        self.area_work = torch.zeros((B_, _lib.SIE_AREA_WORK), dtype=torch.int64, device=dev)
         self.anomaly = torch.zeros((B_, MA, Ts), dtype=f64, device=dev)
         self.links = torch.zeros((B_, MA, MA), dtype=f64, device=dev)
         self.strength = torch.zeros((B_, MA), dtype=f64, device=dev)
