@@ -39,7 +39,7 @@ extern "C" {
 #define SIE_JOB_FEW_AREAS 2     /* ComplexNetworks.py:212/:278 would raise ValueError (<2 areas) */
 #define SIE_JOB_CAPACITY 3      /* more areas / nodes than the caller-provided capacity */
 
-#define SIE_AREA_WORK 16        /* uint64 profiling counters per job written by sie_area_level */
+#define SIE_AREA_WORK 32        /* uint64 profiling counters per job written by sie_area_level */
 
 int sie_abi_version(void);
 const char* sie_last_error(void);

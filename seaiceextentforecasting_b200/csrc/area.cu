@@ -2,95 +2,102 @@
 // Reference: Network.area_level, ComplexNetworks.py:49-278 (semantics restated in SURVEY.md App. A).
 //
 // The algorithm is sequential per network (every decision consumes cells later decisions could have used),
-// so one persistent CTA owns one network and B networks run side by side.  Inside a step the work is
-// parallel: every frontier cell's mean correlation with the area (step 1) and every row of the
-// hypothetical merged area (step 2) is a numpy-order pairwise sum evaluated by an 8-lane group (lane j =
-// numpy's accumulator j), so the float comparisons `mean > tau` / first-max pick the same cell as the
-// reference when fed the same R.  Candidate order (direction-major, then position in the area list,
-// duplicates kept) only matters for ties; it is carried as a per-cell key instead of materialising the
-// reference's candidate list.  Integer state lives in shared memory (global scratch for big grids).
+// so one persistent CTA owns one network and B networks run side by side.  Every growth / merge decision is a
+// float comparison of a numpy-order pairwise sum, so the sums are evaluated in numpy's order (8 strided
+// accumulators per <=128-element leaf, recursive halving above) and the comparisons `mean > tau` / first-max
+// pick the same cell as the reference when fed the same R.  Candidate order (direction-major, then position in
+// the area list, duplicates kept) only matters for ties; it is carried as a per-cell key instead of
+// materialising the reference's candidate list.
 //
-// Latency engineering (the kernel is bound by its chain of dependent steps, not by bandwidth):
-//  * step 1 keeps, per frontier cell, numpy's 8 accumulators + the <8-element tail of its correlation list in
-//    shared memory.  While the area has <= 128 cells (one pairwise leaf) adding a cell appends ONE correlation per
-//    frontier cell (one gather, one L2 round trip per growth step) and the mean is re-assembled from the
-//    accumulators in numpy's order, bit-identical to summing the whole list again.  Larger areas fall back to
-//    re-summing gathered lists.
-//  * step 2 keeps a dense list-order copy D[p][q] = R[best_p][best_q] of the current largest area, extended when
-//    a neighbour is merged, so the O(n^2) "mean of row means" statistic of every hypothetical merge streams
-//    contiguous rows instead of re-gathering the best x best block for every candidate and round.
-// No roofline fraction is claimed for this kernel; see DESIGN.md.
+// The kernel is bound by its chain of dependent steps (one step = one cell added / one merge decided), so the
+// design minimises the critical path of a step rather than bytes:
+//  * step 1, areas of <= 128 cells (one pairwise leaf): every frontier cell owns a slot = one thread.  The slot
+//    keeps numpy's 8 accumulators, the <8-element tail and the running sum in shared memory; adding a member
+//    appends ONE correlation per slot (one gather, issued right after the winner is known) and one add.  A
+//    dedicated warp updates the integer state and builds the state of the <=3 new frontier cells (one 8-lane
+//    group each, all gathers in flight together) while the slot gathers are outstanding.  The CTA-wide argmax is
+//    two levels of redux.sync on an order-preserving integer image of (mean, tie-break key): ~300 cycles.
+//    Larger areas re-sum gathered lists (8-lane groups, lane j = accumulator j).
+//  * step 2 keeps a dense row-major list-order copy D[p][q] = R[best_p][best_q] of the current largest area,
+//    extended when a neighbour is merged, so the O(n^2) "mean of row means" statistic of every hypothetical
+//    merge streams contiguous rows (8 lanes read 64 contiguous bytes) instead of re-gathering the best x best
+//    block for every candidate and round.
+// Integer state and the per-area tables live in shared memory; arrays that do not fit (big grids) fall back to
+// global scratch one by one.  No roofline fraction is claimed for this kernel; see DESIGN.md.
 #include "common.cuh"
 
 namespace {
 
 constexpr int NT = 512;
+constexpr int NW = NT / 32;
 constexpr int NG = NT / 8;          // 8-lane groups per CTA
-constexpr int FCAP = NT;           // frontier slots with incremental state: one thread per slot
+constexpr int FCAP = 256;          // frontier slots with incremental state: slot s is owned by thread s
+constexpr int BKW = NW - 1;        // the warp that updates integer state and initialises new slots
+constexpr int LEAF = 128;          // numpy's pairwise block size
 constexpr int DCAP_MAX = 1024;     // rows/cols of the dense best-area sub-matrix
 constexpr int MAXCH = 32;          // neighbour areas evaluated per chunk of a merge round
 constexpr uint32_t NOKEY = 0xffffffffu;
 constexpr unsigned long long NOKEY64 = ~0ull;
+constexpr unsigned FULL = 0xffffffffu;
+static_assert(FCAP <= NT - 32, "slot threads and the bookkeeping warp must be distinct");
 
-struct AreaScratch {   // per-job global scratch (byte offsets computed on host and device the same way)
-  int32_t* s1_cells;   // [C] step-1 member cells, area after area
-  int32_t* ibuf;       // [6*C] fallback for the shared-memory integer arrays
-  int32_t* nbuf;       // [C] neighbour-area node lists (step 2)
-  double* rowmean;     // [RM] row means of hypothetical areas
-  double* dmat;        // [dcap*dcap] dense list-order copy of R restricted to the current best area (step 2)
-  int32_t* a_start;    // [MA] per step-1 area (segment)
-  int32_t* a_len;      // [MA]
-  int32_t* seg_next;   // [MA]
-  int32_t* tail;       // [MA]
-  int32_t* size;       // [MA] cells in the (merged) area headed by this key; 0 when absorbed
-  int32_t* fin;        // [MA]
-  int32_t* nlist;      // [MA] neighbour keys discovered this round
-  int32_t* noff;       // [MA+1] offsets of neighbour node lists in nbuf
-  unsigned long long* okey;  // [MA]
-  double* stat;        // [MA]
-};
+// which arrays live in global scratch instead of shared memory (bit set = global)
+enum : int { PL_LAB = 1, PL_FKEY = 2, PL_FLIST = 4, PL_HN = 8, PL_HC = 16, PL_CNL = 32, PL_KNL = 64, PL_AREA = 128 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline size_t rm_cap(int C) { return (size_t)4 * C + 1024; }
 __host__ __device__ inline int d_cap(int C) { return C < DCAP_MAX ? C : DCAP_MAX; }
+__host__ __device__ inline size_t area_tab_bytes(int MA) {       // 12 int32 tables + okey + stat
+  return 12 * align_up(sizeof(int32_t) * (size_t)(MA + 1), 16) + 2 * align_up(sizeof(double) * (size_t)MA, 16);
+}
+__host__ __device__ inline size_t self_cap(int C) { return (size_t)2 * C + 64; }
+__host__ __device__ inline size_t slot_bytes() { return sizeof(double) * (18 * FCAP) + sizeof(int32_t) * 2 * FCAP; }
 __host__ __device__ inline size_t scratch_per_job(int C, int MA) {
   size_t s = 0;
   s += align_up(sizeof(int32_t) * (size_t)C, 256);          // s1_cells
-  s += align_up(sizeof(int32_t) * (size_t)6 * C, 256);      // ibuf
-  s += align_up(sizeof(int32_t) * (size_t)C, 256);          // nbuf
+  s += align_up(sizeof(int32_t) * (size_t)7 * C, 256);      // fallback for the shared-memory integer arrays
   s += align_up(sizeof(double) * rm_cap(C), 256);           // rowmean
-  s += align_up(sizeof(double) * (size_t)d_cap(C) * d_cap(C), 256);   // dmat
-  s += 8 * align_up(sizeof(int32_t) * (size_t)(MA + 1), 256);
-  s += 2 * align_up(sizeof(double) * (size_t)MA, 256);
-  return s;
-}
-__device__ inline AreaScratch carve(unsigned char* p, int C, int MA) {
-  AreaScratch s;
-  auto take = [&](size_t bytes) { unsigned char* r = p; p += align_up(bytes, 256); return r; };
-  s.s1_cells = (int32_t*)take(sizeof(int32_t) * (size_t)C);
-  s.ibuf = (int32_t*)take(sizeof(int32_t) * (size_t)6 * C);
-  s.nbuf = (int32_t*)take(sizeof(int32_t) * (size_t)C);
-  s.rowmean = (double*)take(sizeof(double) * rm_cap(C));
-  s.dmat = (double*)take(sizeof(double) * (size_t)d_cap(C) * d_cap(C));
-  s.a_start = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  s.a_len = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  s.seg_next = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  s.tail = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  s.size = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  s.fin = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  s.nlist = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  s.noff = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  s.okey = (unsigned long long*)take(sizeof(double) * (size_t)MA);
-  s.stat = (double*)take(sizeof(double) * (size_t)MA);
+  s += align_up(sizeof(double) * ((size_t)d_cap(C) * d_cap(C) + 128), 256);   // dmat (+ read-ahead pad)
+  s += align_up(area_tab_bytes(MA), 256);                   // fallback for the per-area tables
+  s += align_up(sizeof(double) * self_cap(C), 256);         // cached self row means of candidate areas
   return s;
 }
 
-// Argmax record, compared branch-free as a 128-bit unsigned number: `hi` is an order-preserving image of the
-// mean (0 = no candidate), `lo` the tie-break priority (larger wins: the bitwise complement of the reference's
-// candidate-list position, so the earliest candidate wins ties) with the candidate index in its low bits.
-struct Pick {
-  unsigned long long hi, lo;
+struct AreaTabs {       // per step-1 area (segment); merged areas are chains of segments
+  int32_t *a_start, *a_len, *seg_next, *tail, *size, *fin, *nlist;
+  int32_t *xoff, *xep, *xrows;     // step 2: column offset of the area's cross block in D, epoch it belongs to, best rows filled
+  int32_t *self_off, *self_sz;     // step 2: cached self row means (offset into selfbuf; valid when self_sz == size)
+  unsigned long long* okey;
+  double* stat;
 };
+__device__ inline AreaTabs carve_tabs(unsigned char* p, int MA) {
+  AreaTabs t;
+  auto take = [&](size_t bytes) { unsigned char* r = p; p += align_up(bytes, 16); return r; };
+  t.a_start = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
+  t.a_len = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
+  t.seg_next = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
+  t.tail = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
+  t.size = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
+  t.fin = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
+  t.nlist = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
+  t.xoff = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
+  t.xep = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
+  t.xrows = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
+  t.self_off = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
+  t.self_sz = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
+  t.okey = (unsigned long long*)take(sizeof(double) * (size_t)MA);
+  t.stat = (double*)take(sizeof(double) * (size_t)MA);
+  return t;
+}
+
+// Argmax record.  `ord` is an order-preserving image of the value (0 = no candidate), `pri` the tie-break
+// priority (larger wins: the bitwise complement of the reference's candidate-list position, so the earliest
+// candidate wins ties); a, b are payload.
+struct Rec {
+  unsigned long long ord, pri;
+  uint32_t a, b;
+};
+__device__ __forceinline__ Rec rec_none() { Rec r; r.ord = 0ull; r.pri = 0ull; r.a = 0u; r.b = 0u; return r; }
 __device__ __forceinline__ unsigned long long ord_of(double x) {      // monotone map double -> u64, never 0
   x = __dadd_rn(x, 0.0);                                               // -0.0 -> +0.0 (they compare equal)
   const unsigned long long u = (unsigned long long)__double_as_longlong(x);
@@ -100,34 +107,52 @@ __device__ __forceinline__ double ord_to_double(unsigned long long o) {
   const unsigned long long u = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
   return __longlong_as_double((long long)u);
 }
-__device__ __forceinline__ Pick pick_max(const Pick& a, const Pick& b) {
-  const bool tb = (b.hi > a.hi) || (b.hi == a.hi && b.lo > a.lo);
-  Pick r;
-  r.hi = tb ? b.hi : a.hi;
-  r.lo = tb ? b.lo : a.lo;
-  return r;
+__device__ __forceinline__ Rec rec_max(const Rec& x, const Rec& y) {
+  const bool ty = (y.ord > x.ord) || (y.ord == x.ord && y.pri > x.pri);
+  return ty ? y : x;
 }
-__device__ __forceinline__ Pick pick_none() { Pick r; r.hi = 0ull; r.lo = 0ull; return r; }
-// CTA-wide argmax; every thread returns the same winner.  `slots` is shared scratch of NT/32 records.
-// `SyncBefore = false` is for callers that already placed a barrier between the previous call's reads and this one.
-template <bool SyncBefore = true>
-__device__ __forceinline__ Pick block_pick(Pick v, Pick* slots) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    Pick w;
-    w.hi = __shfl_xor_sync(0xffffffffu, v.hi, o);
-    w.lo = __shfl_xor_sync(0xffffffffu, v.lo, o);
-    v = pick_max(v, w);
+// Warp argmax by lexicographic redux.sync over 32-bit words (PW = 32-bit words of `pri` that matter: 1 -> only
+// the high word).  Every lane returns the winner.
+template <int PW>
+__device__ __forceinline__ Rec warp_arg(const Rec& r) {
+  const uint32_t w0 = (uint32_t)(r.ord >> 32), w1 = (uint32_t)r.ord;
+  const uint32_t w2 = (uint32_t)(r.pri >> 32), w3 = (uint32_t)r.pri;
+  const uint32_t m0 = __reduce_max_sync(FULL, w0);
+  bool ok = (w0 == m0);
+  const uint32_t m1 = __reduce_max_sync(FULL, ok ? w1 : 0u);
+  ok = ok && (w1 == m1);
+  const uint32_t m2 = __reduce_max_sync(FULL, ok ? w2 : 0u);
+  ok = ok && (w2 == m2);
+  uint32_t m3 = 0u;
+  if (PW > 1) {
+    m3 = __reduce_max_sync(FULL, ok ? w3 : 0u);
+    ok = ok && (w3 == m3);
   }
-  if (SyncBefore) __syncthreads();     // slots may still be read from the previous call
-  if ((threadIdx.x & 31) == 0) slots[threadIdx.x >> 5] = v;
+  const int src = __ffs(__ballot_sync(FULL, ok)) - 1;      // never empty: the maximal lane survives every stage
+  Rec o;
+  o.ord = ((unsigned long long)m0 << 32) | m1;
+  o.pri = ((unsigned long long)m2 << 32) | m3;
+  o.a = __shfl_sync(FULL, r.a, src);
+  o.b = __shfl_sync(FULL, r.b, src);
+  return o;
+}
+struct RecSlot { unsigned long long ord, pri; uint32_t a, b, pad0, pad1; };   // 32 bytes
+// CTA-wide argmax; every thread returns the same winner.  `slots` is shared scratch [2][NW]; `par` alternates so
+// the next call never overwrites records a slow warp is still reading (one barrier per call).
+template <int PW>
+__device__ __forceinline__ Rec block_arg(const Rec& v, RecSlot* slots, int& par) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const Rec w = warp_arg<PW>(v);
+  RecSlot* s = slots + par * NW;
+  if (lane == 0) { s[warp].ord = w.ord; s[warp].pri = w.pri; s[warp].a = w.a; s[warp].b = w.b; }
   __syncthreads();
-  Pick r = slots[0];
-#pragma unroll
-  for (int w = 1; w < NT / 32; ++w) r = pick_max(r, slots[w]);
-  return r;
+  Rec t = rec_none();
+  if (lane < NW) { t.ord = s[lane].ord; t.pri = s[lane].pri; t.a = s[lane].a; t.b = s[lane].b; }
+  par ^= 1;
+  return warp_arg<PW>(t);
 }
 
+template <bool ONCHIP>
 __global__ void __launch_bounds__(NT, 1)
 k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil_all,
              const int32_t* __restrict__ node_cell_all, const int32_t* __restrict__ cell_node_all,
@@ -136,14 +161,18 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
              int32_t* __restrict__ area_cells_all, int32_t* __restrict__ area_start_all,
              int32_t* __restrict__ area_key_all, int32_t* __restrict__ n_areas_all,
              int32_t* __restrict__ label_all, int32_t* __restrict__ status_all,
-             unsigned char* __restrict__ scratch_all, size_t scratch_stride, int use_smem,
+             unsigned char* __restrict__ scratch_all, size_t scratch_stride, int place_arg,
              unsigned long long* __restrict__ work_all) {
-  extern __shared__ __align__(16) int32_t smem_i[];
-  __shared__ Pick slots[NT / 32];
+  constexpr int MAXD = ONCHIP ? 6 : 16;        // pairwise tree depth: lists are <= C cells, C < 8192 when ONCHIP
+  const int place = ONCHIP ? 0 : place_arg;   // ONCHIP: every array in shared memory (pointers known to be shared)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ RecSlot rslots[2 * NW];
   __shared__ int sh_i[8];
   __shared__ int sh_koff[MAXCH + 1], sh_uoff[MAXCH + 1];
+  __shared__ int sh_goff[MAXCH + 1], sh_soff[MAXCH + 1], sh_xo[MAXCH], sh_r0[MAXCH], sh_so[MAXCH];
+  __shared__ int sh_x[4];
   __shared__ unsigned long long sh_work;
-  __shared__ unsigned long long ph[12];   // per-phase SM cycles (thread 0's view), reported through work[4..15]
+  __shared__ unsigned long long ph[16];   // per-phase SM cycles (thread 0's view), reported through work[4..15]
   long long tick_last = 0;
 #define TICK(i)                                                        \
   do {                                                                 \
@@ -153,10 +182,18 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
       tick_last = t__;                                                 \
     }                                                                  \
   } while (0)
-  unsigned long long wk = 0;   // correlations consumed (algorithmic gathers), tallied by lane 0 of each group
+  unsigned long long wk = 0;   // correlations consumed (algorithmic gathers)
+  unsigned long long bph[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // bookkeeping-warp phase cycles (its lane 0), work[16..23]
+  long long btick = 0;
+#define BTICK(i)                                                       \
+  do {                                                                 \
+    const long long t__ = clock64();                                   \
+    bph[i] += (unsigned long long)(t__ - btick);                       \
+    btick = t__;                                                       \
+  } while (0)
 
   const int b = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = tid >> 3, j = tid & 7;
   const unsigned gmask = 0xffu << (lane & 24);
   const int C = X * Y;
@@ -169,26 +206,42 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   int32_t* out_start = area_start_all + (size_t)b * (MA + 1);
   int32_t* out_key = area_key_all + (size_t)b * MA;
   int32_t* out_label = label_all + (size_t)b * C;
+  int par = 0;
 
-  AreaScratch S = carve(scratch_all + (size_t)b * scratch_stride, C, MA);
-  // dynamic shared memory: [frontier-slot state: facc 8*FCAP f64 | ftail 8*FCAP f64 | fnan FCAP i32][6*C i32]
-  double* facc = reinterpret_cast<double*>(smem_i);     // [8][FCAP] numpy accumulator j of slot s at j*FCAP+s
-  double* ftail = facc + 8 * FCAP;                       // [8][FCAP] tail element t of slot s at t*FCAP+s
-  int32_t* fnan = reinterpret_cast<int32_t*>(ftail + 8 * FCAP);   // [FCAP] NaN entries seen by slot s
-  int32_t* ib = use_smem ? fnan + FCAP : S.ibuf;
-  int32_t* lab = ib;                      // [C] area key of each cell, -1 = unassigned
-  uint32_t* fkey = (uint32_t*)(ib + C);   // [C] frontier key (step 1)
-  int32_t* flist = ib + 2 * C;            // [C] frontier cells (step 1)
-  int32_t* hn = ib + 3 * C;               // [C] node list of the current area (step 1) / best area (step 2)
-  int32_t* hc = ib + 4 * C;               // [C] cell list of the best area (step 2)
-  int32_t* cnl = ib + 5 * C;              // [C] local copy of cell -> node
-  int32_t* knl = (use_smem >= 2) ? ib + 6 * C : S.nbuf;   // [C] node lists of the neighbour areas (step 2)
-  const int32_t* cnode = cnl;
+  // ---- global scratch of this job
+  unsigned char* gp = scratch_all + (size_t)b * scratch_stride;
+  auto gtake = [&](size_t bytes) { unsigned char* r = gp; gp += align_up(bytes, 256); return r; };
+  int32_t* s1_cells = (int32_t*)gtake(sizeof(int32_t) * (size_t)C);   // step-1 member cells, area after area
+  int32_t* ibuf = (int32_t*)gtake(sizeof(int32_t) * (size_t)7 * C);
+  double* rowmean = (double*)gtake(sizeof(double) * rm_cap(C));
   const int dcap = d_cap(C);
-  double* D = S.dmat;
+  double* D = (double*)gtake(sizeof(double) * ((size_t)dcap * dcap + 128));
+  unsigned char* gtabs = gtake(area_tab_bytes(MA));
+  double* selfbuf = (double*)gtake(sizeof(double) * self_cap(C));
+  // ---- shared memory: slot state | per-area tables | integer arrays (whatever `place` keeps on chip)
+  unsigned char* sp = smem_raw;
+  auto stake = [&](size_t bytes) { unsigned char* r = sp; sp += align_up(bytes, 16); return r; };
+  double* facc = (double*)stake(sizeof(double) * 8 * FCAP);    // [8][FCAP] numpy accumulator q of slot s at q*FCAP+s
+  double* ftail = (double*)stake(sizeof(double) * 8 * FCAP);   // [8][FCAP] tail element t of slot s at t*FCAP+s
+  double* sres = (double*)stake(sizeof(double) * FCAP);        // running pairwise sum of the slot's list
+  double* smean = (double*)stake(sizeof(double) * FCAP);       // its nanmean
+  int32_t* snan = (int32_t*)stake(sizeof(int32_t) * FCAP);     // NaN entries seen
+  int32_t* srow = (int32_t*)stake(sizeof(int32_t) * FCAP);     // node of the slot's cell, -1 = dead slot
+  AreaTabs S = carve_tabs((place & PL_AREA) ? gtabs : stake(area_tab_bytes(MA)), MA);
+  auto iarr = [&](int bit, int idx) -> int32_t* {
+    return (place & bit) ? ibuf + (size_t)idx * C : (int32_t*)stake(sizeof(int32_t) * (size_t)C);
+  };
+  int32_t* lab = iarr(PL_LAB, 0);                      // [C] area key of each cell, -1 = unassigned
+  uint32_t* fkey = (uint32_t*)iarr(PL_FKEY, 1);        // [C] frontier key (step 1)
+  int32_t* flist = iarr(PL_FLIST, 2);                  // [C] frontier cell of each slot (step 1), -1 = dead
+  int32_t* hn = iarr(PL_HN, 3);                        // [C] node list of the current area (step 1) / best area (step 2)
+  int32_t* hc = iarr(PL_HC, 4);                        // [C] cell list of the best area (step 2)
+  int32_t* cnl = iarr(PL_CNL, 5);                      // [C] local copy of cell -> node
+  int32_t* knl = iarr(PL_KNL, 6);                      // [C] node lists of the neighbour areas (step 2)
+  const int32_t* cnode = cnl;
 
   for (int c = tid; c < C; c += NT) { lab[c] = -1; fkey[c] = NOKEY; out_label[c] = -1; cnl[c] = cnode_g[c]; }
-  if (tid < 12) ph[tid] = 0ull;
+  if (tid < 16) ph[tid] = 0ull;
   if (tid == 0) { n_areas_all[b] = 0; out_start[0] = 0; sh_work = 0ull; if (work_all) work_all[SIE_AREA_WORK * b] = 0ull; }
   __syncthreads();
   if (first_nan_cell[b] < 0) {            // :50-51 IndexError in the reference
@@ -197,15 +250,45 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   }
   if (status_all[b] == SIE_JOB_CAPACITY) return;   // K1 already flagged this job
 
-  // ---- step-1 helpers --------------------------------------------------------------------------------
-  // gen_area_neighbours :80-94 for one member cell `cc` at list position `p` (no lat-lon wrap here): warp 0,
-  // lane d < 4 = direction.  New frontier cells are appended at flist[cnt..]; returns the new count.
-  auto frontier_add = [&](int cc, int p, int cnt) -> int {
+  // ---- step-1 helpers (bookkeeping warp only) -----------------------------------------------------------
+  // State of slot s (frontier cell with node `fnode` vs the first n <= 128 member nodes hn[0..n)) by one 8-lane
+  // group: lane j builds numpy's accumulator j = a[j] + a[8+j] + ... over the full groups of 8, keeps tail element
+  // j, and the group assembles the pairwise sum in numpy's order.  All gathers are issued before the first add.
+  auto init_slot = [&](int s, int fnode, int n) {
+    const double* row = R + (size_t)fnode * ldn;
+    const int ngrp = n >> 3, nt = n & 7;
+    double r, tv;
+    int nanc = 0;
+    sie_pw_lane8_any([&](int i) { return __ldg(row + hn[i]); }, 0, n, ngrp, nt, j, r, tv, nanc);
+    facc[j * FCAP + s] = r;
+    ftail[j * FCAP + s] = tv;
+    double res = 0.0;
+    if (ngrp > 0) {     // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) : xor-butterfly inside the group (IEEE add commutes)
+      res = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+      res = __dadd_rn(res, __shfl_xor_sync(gmask, res, 2));
+      res = __dadd_rn(res, __shfl_xor_sync(gmask, res, 4));
+    }
+    for (int t = 0; t < nt; ++t) res = __dadd_rn(res, __shfl_sync(gmask, tv, t, 8));   // tail, left to right
+    nanc += __shfl_xor_sync(gmask, nanc, 1);
+    nanc += __shfl_xor_sync(gmask, nanc, 2);
+    nanc += __shfl_xor_sync(gmask, nanc, 4);
+    if (j == 0) {
+      sres[s] = res;
+      snan[s] = nanc;
+      srow[s] = fnode;
+      smean[s] = res / (double)(n - nanc);
+    }
+  };
+  // gen_area_neighbours :80-94 for the member cell `m` at list position `p` (no lat-lon wrap here): lane d < 4 =
+  // direction.  New frontier cells take the free slot `hole` first, then slots nf, nf+1, ...; with `do_init` their
+  // incremental state over the `nmem` members is built.  Returns the new slot high-water mark; `fits` = all slots
+  // are below FCAP.
+  auto bk_add = [&](int m, int p, int nmem, int hole, int nf, bool do_init, bool& fits) -> int {
     bool isnew = false;
     int f = -1;
     if (lane < 4) {
       const int d = lane;
-      const int ci = cc / Y, cj = cc - ci * Y;
+      const int ci = m / Y, cj = m - ci * Y;
       const int a = ci + (d == 0 ? -1 : (d == 1 ? 1 : 0));
       const int q = cj + (d == 2 ? -1 : (d == 3 ? 1 : 0));
       if (a >= 0 && a < X && q >= 0 && q < Y) {
@@ -220,67 +303,34 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         if (key < old) fkey[f] = key;
       }
     }
-    const unsigned mnew = __ballot_sync(0xffffffffu, isnew);
-    if (isnew) flist[cnt + __popc(mnew & ((1u << lane) - 1u))] = f;
+    const unsigned mnew = __ballot_sync(FULL, isnew);
+    const int cntnew = __popc(mnew);
+    BTICK(1);                             // membership writes + neighbour detection
+    int myslot = -1;
+    if (isnew) {
+      const int r = __popc(mnew & ((1u << lane) - 1u));
+      myslot = (hole >= 0) ? (r == 0 ? hole : nf + r - 1) : nf + r;
+      flist[myslot] = f;
+    }
+    const int nf_new = nf + cntnew - ((hole >= 0 && cntnew > 0) ? 1 : 0);
+    if (hole >= 0 && cntnew == 0 && lane == 0) { flist[hole] = -1; if (hole < FCAP) srow[hole] = -1; }
+    fits = (nf_new <= FCAP);
     __syncwarp();
-    return cnt + __popc(mnew);
-  };
-  // numpy pairwise state of slot s (its frontier cell vs the first n <= 128 member cells): 8-lane group, lane j
-  // builds accumulator j = a[j] + a[8+j] + ... over the full groups of 8 and fetches tail element j.
-  auto init_slot = [&](int s, int n) {
-    const double* row = R + (size_t)cnode[flist[s]] * ldn;
-    const int ngrp = n >> 3, nt = n & 7;
-    double v[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) v[q] = (q < ngrp) ? __ldg(row + hn[8 * q + j]) : 0.0;
-    double tv = (j < nt) ? __ldg(row + hn[8 * ngrp + j]) : 0.0;
-    int nanc = 0;
-    if (tv != tv) { tv = 0.0; ++nanc; }
-    double r = 0.0;
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      if (q < ngrp) {
-        double x = v[q];
-        if (x != x) { x = 0.0; ++nanc; }
-        r = (q == 0) ? x : __dadd_rn(r, x);
-      }
+    if (do_init && fits && cntnew > 0) {
+      const int gi = lane >> 3;
+      unsigned mm = mnew;
+      for (int r = 0; r < gi; ++r) mm &= mm - 1u;          // drop the gi lowest set bits
+      const int src = mm ? (__ffs(mm) - 1) : 0;
+      const int cell = __shfl_sync(FULL, f, src);
+      const int slot = __shfl_sync(FULL, myslot, src);
+      BTICK(2);                           // slot assignment
+      if (mm) init_slot(slot, cnode[cell], nmem);
+      __syncwarp();
+      BTICK(3);                           // new-slot state (gathers + numpy-order sums)
+      bph[5] += 1;
     }
-    facc[j * FCAP + s] = r;
-    ftail[j * FCAP + s] = tv;
-    nanc += __shfl_xor_sync(gmask, nanc, 1);
-    nanc += __shfl_xor_sync(gmask, nanc, 2);
-    nanc += __shfl_xor_sync(gmask, nanc, 4);
-    if (j == 0) fnan[s] = nanc;
-  };
-  // append element index n_old (value v) to slot s
-  auto fold_slot = [&](int s, double v, int n_old) {
-    if (v != v) { v = 0.0; fnan[s] += 1; }
-    const int t = n_old & 7;
-    if (t == 7) {                         // a group of 8 is complete: it joins the accumulators
-      if (n_old == 7) {
-#pragma unroll
-        for (int q = 0; q < 7; ++q) facc[q * FCAP + s] = ftail[q * FCAP + s];
-        facc[7 * FCAP + s] = v;
-      } else {
-#pragma unroll
-        for (int q = 0; q < 7; ++q) facc[q * FCAP + s] = __dadd_rn(facc[q * FCAP + s], ftail[q * FCAP + s]);
-        facc[7 * FCAP + s] = __dadd_rn(facc[7 * FCAP + s], v);
-      }
-    } else {
-      ftail[t * FCAP + s] = v;
-    }
-  };
-  // np.nanmean of slot s's list of n <= 128 correlations, in numpy's pairwise order
-  auto eval_slot = [&](int s, int n) -> double {
-    const int nt = n & 7;
-    double res = 0.0;
-    if (n >= 8) {
-      const double a0 = facc[s], a1 = facc[FCAP + s], a2 = facc[2 * FCAP + s], a3 = facc[3 * FCAP + s];
-      const double a4 = facc[4 * FCAP + s], a5 = facc[5 * FCAP + s], a6 = facc[6 * FCAP + s], a7 = facc[7 * FCAP + s];
-      res = __dadd_rn(__dadd_rn(__dadd_rn(a0, a1), __dadd_rn(a2, a3)), __dadd_rn(__dadd_rn(a4, a5), __dadd_rn(a6, a7)));
-    }
-    for (int t = 0; t < nt; ++t) res = __dadd_rn(res, ftail[t * FCAP + s]);
-    return res / (double)(n - fnan[s]);
+    __syncwarp();
+    return nf_new;
   };
 
   // =============================================================== step 1 (:154-196)
@@ -313,15 +363,13 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         if (!(mx > tau)) dir = -1;
       }
     }
-    Pick cand = pick_none();
-    if (dir >= 0) { cand.hi = 1ull; cand.lo = ~(unsigned long long)(unsigned)c; }   // earliest cell wins
-    const Pick win = block_pick(cand, slots);
+    Rec cand = rec_none();
+    if (dir >= 0) { cand.ord = 1ull; cand.pri = (unsigned long long)(~(uint32_t)c) << 32; cand.a = (uint32_t)c; cand.b = (uint32_t)dir; }
+    const Rec sw = block_arg<1>(cand, rslots, par);   // earliest cell wins
     TICK(0);                              // seed search
-    if (win.hi == 0ull) { c0 += NT; continue; }
-    const int seed = (int)(unsigned)(~win.lo);
-    if (tid == seed - c0) sh_i[0] = dir;
-    __syncthreads();
-    const int sd = sh_i[0];
+    if (sw.ord == 0ull) { c0 += NT; continue; }
+    const int seed = (int)sw.a;
+    const int sd = (int)sw.b;
     const int si = seed / Y, sj = seed - si * Y;
     int ni = si + (sd == 0 ? -1 : (sd == 1 ? 1 : 0));
     int nj = sj + (sd == 2 ? -1 : (sd == 3 ? 1 : 0));
@@ -335,104 +383,126 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
     // --- new area k = nA : [seed, nbr], then expand (:120-152)
     const int k = nA;
     int n = 2, nf = 0;
-    __syncthreads();
-    if (tid < 32) {                       // warp 0 owns the integer bookkeeping
+    bool fast = true;                     // incremental slot state valid (uniform across the CTA)
+    __syncthreads();                      // every thread has read lab[nbr] before it changes
+    if (warp == BKW) {
       if (lane == 0) {
         lab[seed] = k; lab[nbr] = k;
         hn[0] = cnode[seed]; hn[1] = cnode[nbr];
-        S.s1_cells[base] = seed; S.s1_cells[base + 1] = nbr;
+        s1_cells[base] = seed; s1_cells[base + 1] = nbr;
       }
       __syncwarp();
-      int cnt = frontier_add(seed, 0, 0);
-      cnt = frontier_add(nbr, 1, cnt);
-      if (lane == 0) sh_i[1] = cnt;
+      bool fits = true, fits2 = true;
+      int cnt = bk_add(seed, 0, 2, -1, 0, true, fits);
+      cnt = bk_add(nbr, 1, 2, -1, cnt, fits, fits2);
+      if (lane == 0) { sh_i[1] = cnt; sh_i[2] = (fits && fits2) ? 1 : 0; }
     }
     __syncthreads();
     nf = sh_i[1];
-    bool fast = (nf <= FCAP);             // incremental accumulators valid (uniform across the CTA)
-    if (fast) {
-      for (int s = g; s < nf; s += NG) init_slot(s, n);
-      __syncthreads();
-    }
-    TICK(3);                              // area creation + first slot states
+    fast = sh_i[2] != 0;
+    TICK(2);                              // area creation + first slot states
     while (nf > 0) {
-      Pick loc = pick_none();
-      if (!fast) ++n_slow;
+      // --- evaluate every frontier cell's mean correlation with the area (:96-118) and pick the maximum
+      Rec loc = rec_none();
       if (fast) {
-        TICK(11);
-        if (tid < nf) {
-          const double mean = eval_slot(tid, n);
-          if (mean == mean) { loc.hi = ord_of(mean); loc.lo = ((unsigned long long)(~fkey[flist[tid]]) << 32) | (unsigned)tid; }
+        int cell = -1;
+        if (tid < nf) cell = flist[tid];
+        if (cell >= 0) {
+          const double mean = smean[tid];
+          if (mean == mean) { loc.ord = ord_of(mean); loc.pri = (unsigned long long)(~fkey[cell]) << 32; loc.a = (uint32_t)tid; loc.b = (uint32_t)cell; }
         }
-        if (tid == 0) wk += (unsigned long long)n * (unsigned long long)nf;
+        const unsigned live = __ballot_sync(FULL, cell >= 0);
+        if (lane == 0) wk += (unsigned long long)n * (unsigned long long)__popc(live);
       } else {
+        ++n_slow;
         for (int q = g; q < nf; q += NG) {
           const int f = flist[q];
+          if (f < 0) continue;
           const double* row = R + (size_t)cnode[f] * ldn;
           int nanc = 0;
-          const double sum = sie_pw_sum8([&](int i) { return __ldg(row + hn[i]); }, n, j, gmask, nanc);
+          const double sum = sie_pw_sum8<MAXD>([&](int i) { return __ldg(row + hn[i]); }, n, j, gmask, nanc);
           if (j == 0) wk += (unsigned long long)n;
           nanc += __shfl_xor_sync(gmask, nanc, 1);
           nanc += __shfl_xor_sync(gmask, nanc, 2);
           nanc += __shfl_xor_sync(gmask, nanc, 4);
           const double mean = sum / (double)(n - nanc);   // np.nanmean: NaN -> 0, divide by the non-NaN count
           if (mean == mean) {
-            Pick cur; cur.hi = ord_of(mean); cur.lo = ((unsigned long long)(~fkey[f]) << 32) | (unsigned)q;
-            loc = pick_max(loc, cur);
+            Rec cur; cur.ord = ord_of(mean); cur.pri = (unsigned long long)(~fkey[f]) << 32; cur.a = (uint32_t)q; cur.b = (uint32_t)f;
+            loc = rec_max(loc, cur);
           }
         }
       }
       TICK(10);                           // evaluate
-      const Pick win2 = block_pick<false>(loc, slots);   // the barrier closing the previous step already ran
+      const Rec win = block_arg<1>(loc, rslots, par);
       TICK(1);                            // argmax
-      if (win2.hi == 0ull || !(ord_to_double(win2.hi) > tau)) break;   // :134 (nanmax of all-NaN is NaN -> stop)
-      const int widx = (int)(unsigned)(win2.lo & 0xffffffffull);
-      const int last = nf - 1;
-      if (tid < 32) {
-        const int m = flist[widx];
-        __syncwarp();
+      if (win.ord == 0ull || !(ord_to_double(win.ord) > tau)) break;   // :134 (nanmax of all-NaN is NaN -> stop)
+      const int widx = (int)win.a;
+      const int m = (int)win.b;
+      const int mnode = cnode[m];
+      const bool fast_upd = fast && (n + 1 <= LEAF);
+      // --- slot owners: the one new correlation of this step, issued before anything else
+      bool own = false;
+      double v = 0.0;
+      if (fast_upd && tid < nf && tid != widx) {
+        const int rn = srow[tid];
+        if (rn >= 0) { own = true; v = __ldg(R + (size_t)rn * ldn + mnode); }
+      }
+      // --- bookkeeping warp: membership, frontier keys, new frontier cells and their slot state
+      if (warp == BKW) {
+        BTICK(0);                         // everything outside the update (evaluate, argmax, waiting)
         if (lane == 0) {
           lab[m] = k;
-          hn[n] = cnode[m];
-          S.s1_cells[base + n] = m;
+          hn[n] = mnode;
+          s1_cells[base + n] = m;
           fkey[m] = NOKEY;
-          flist[widx] = flist[last];
-          sh_i[4] = m;
         }
         __syncwarp();
-        const int cnt = frontier_add(m, n, last);
-        if (lane == 0) sh_i[1] = cnt;
-      } else if (tid < 64 && fast && widx != last) {   // slot state follows the cell moved into the hole
-        const int l2 = lane;
-        if (l2 < 8) facc[l2 * FCAP + widx] = facc[l2 * FCAP + last];
-        else if (l2 < 16) ftail[(l2 - 8) * FCAP + widx] = ftail[(l2 - 8) * FCAP + last];
-        else if (l2 == 16) fnan[widx] = fnan[last];
+        bool fits = true;
+        const int cnt = bk_add(m, n, n + 1, widx, nf, fast_upd, fits);
+        if (lane == 0) { sh_i[1] = cnt; sh_i[2] = (fast_upd && fits) ? 1 : 0; }
+        BTICK(4);
+      }
+      if (own) {                          // append element index n (value v) to the slot's list
+        int nn = snan[tid];
+        if (v != v) { v = 0.0; ++nn; snan[tid] = nn; }
+        const int t = n & 7;
+        double res;
+        if (t == 7) {                     // a group of 8 is complete: it joins the accumulators
+          double a[8];
+          if (n == 7) {
+#pragma unroll
+            for (int q = 0; q < 7; ++q) a[q] = ftail[q * FCAP + tid];
+            a[7] = v;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 7; ++q) a[q] = __dadd_rn(facc[q * FCAP + tid], ftail[q * FCAP + tid]);
+            a[7] = __dadd_rn(facc[7 * FCAP + tid], v);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) facc[q * FCAP + tid] = a[q];
+          res = __dadd_rn(__dadd_rn(__dadd_rn(a[0], a[1]), __dadd_rn(a[2], a[3])),
+                          __dadd_rn(__dadd_rn(a[4], a[5]), __dadd_rn(a[6], a[7])));
+        } else {
+          ftail[t * FCAP + tid] = v;
+          res = __dadd_rn(sres[tid], v);
+        }
+        sres[tid] = res;
+        smean[tid] = res / (double)(n + 1 - nn);
+        TICK(11);                         // owner path: gather latency + fold (thread 0's slot)
       }
       __syncthreads();
-      TICK(2);                            // frontier update
       nf = sh_i[1];
-      if (fast) {
-        if (n + 1 > 128 || nf > FCAP) {
-          fast = false;                   // beyond one pairwise leaf: re-sum gathered lists from here on
-        } else {
-          const int mnode = hn[n];
-          // new frontier cells (slots last..nf-1): build their state over the n+1 member cells; use the highest
-          // groups, which rarely own an old slot as well
-          for (int s = last + (NG - 1 - g); s < nf; s += NG) init_slot(s, n + 1);
-          // old frontier cells: append the correlation with the new member
-          if (tid < last) fold_slot(tid, __ldg(R + (size_t)cnode[flist[tid]] * ldn + mnode), n);
-        }
-      }
+      fast = sh_i[2] != 0;
       ++n;
       ++n_steps;
-      __syncthreads();
-      TICK(3);                            // one gather per frontier cell + new-slot states
+      TICK(3);                            // frontier update + one gather per frontier cell + new-slot states
     }
     __syncthreads();
-    for (int q = tid; q < nf; q += NT) fkey[flist[q]] = NOKEY;
+    for (int q = tid; q < nf; q += NT) { const int f = flist[q]; if (f >= 0) fkey[f] = NOKEY; }
     if (tid == 0) {
       S.a_start[k] = base; S.a_len[k] = n; S.seg_next[k] = -1; S.tail[k] = k; S.size[k] = n; S.fin[k] = 0;
       S.okey[k] = NOKEY64;
+      S.xep[k] = 0; S.self_sz[k] = 0;
     }
     base += n;
     nA = k + 1;
@@ -449,27 +519,32 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   // `taken` is now "belongs to a finalised area"; lab[] keeps tracking the current owner key.
   int cur_best = -1, nb = 0;     // best area whose lists are materialised in hn/hc
   const size_t RM = rm_cap(C);
+  const int ld = dcap;           // row stride of D
   bool d_ok = false;             // dense block valid for the first nb member cells
-  // Dense list-order copy of R restricted to the best area, stored by diagonals: element (p, q), q > p, lives at
-  // D[(q-p-1)*dcap + p], so thread p walking its row p+1, p+2, ... reads addresses consecutive with its
-  // neighbours' (coalesced) in the row-mean pass.  extend_D adds the pairs with from <= q < to.
+  int epoch = 0, xtop = ld;      // cross-block column allocator (downwards from ld), restarted when the best area changes
+  int self_top = 0;              // bump allocator of selfbuf
+  // D: dense list-order copy of R for the current best area.  Row p = best member p.  Columns [0, nb): element
+  // (p, q), q > p, = R[best_p][best_q].  Columns [xoff_k, xoff_k + |k|): the cross block R[best_p][k_q] of neighbour
+  // area k, kept while the best area only grows, so a hypothetical merged row p is TWO contiguous runs of row p.
+  // One 8-lane group per row; extend_D adds the pairs with from <= q < to.
   auto extend_D = [&](int from, int to) {
     d_ok = (to <= dcap) && (from == 0 || d_ok);
     if (!d_ok) return;
-    for (int i0 = 0; i0 < to - 1; i0 += 8) {            // 8 diagonals per pass: 8 gathers in flight per thread
-      const int plo = max(0, from - 8 - i0);
-      for (int pp = plo + tid; pp < to - 1 - i0; pp += NT) {
-        const double* row = R + (size_t)hn[pp] * ldn;
+    for (int p = g; p < to - 1; p += NG) {
+      const double* row = R + (size_t)hn[p] * ldn;
+      double* drow = D + (size_t)p * ld;
+      for (int q0 = max(from, p + 1); q0 < to; q0 += 64) {   // 8 gathers in flight per lane
         double v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int q = pp + 1 + i0 + u;
-          v[u] = (q < to && q >= from) ? __ldg(row + hn[q]) : 0.0;
+          const int q = min(q0 + 8 * u + j, to - 1);
+          v[u] = __ldg(row + hn[q]);
         }
+        sie_fence_regs<8>(v);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int q = pp + 1 + i0 + u;
-          if (q < to && q >= from) D[(size_t)(i0 + u) * dcap + pp] = v[u];
+          const int q = q0 + 8 * u + j;
+          if (q < to) drow[q] = v[u];
         }
       }
     }
@@ -477,31 +552,33 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   };
   while (true) {
     // --- largest not-yet-final area, first key on ties (:207-212)
-    Pick loc = pick_none();
+    Rec loc = rec_none();
     for (int k = tid; k < nA; k += NT) {
       const int sz = S.size[k];
       if (sz > 0) {             // still a key of V
-        Pick cur; cur.hi = ord_of(S.fin[k] ? 0.0 : (double)sz); cur.lo = ~(unsigned long long)(unsigned)k;
-        loc = pick_max(loc, cur);
+        Rec cur; cur.ord = 1ull + (unsigned long long)(S.fin[k] ? 0 : sz); cur.pri = (unsigned long long)(~(uint32_t)k) << 32;
+        cur.a = (uint32_t)k; cur.b = 0u;
+        loc = rec_max(loc, cur);
       }
     }
-    const Pick bw = block_pick(loc, slots);
-    if (bw.hi == 0ull || ord_to_double(bw.hi) == 0.0) break;   // no areas at all (:212) or all finalised
-    const int best = (int)(unsigned)(~bw.lo);
+    const Rec bw = block_arg<1>(loc, rslots, par);
+    if (bw.ord <= 1ull) break;   // no areas at all (:212) or all finalised
+    const int best = (int)bw.a;
     ++n_rounds;
     if (best != cur_best) {                    // materialise V[best] in list order
       int off = 0;
       for (int s = best; s >= 0; s = S.seg_next[s]) {
         const int st = S.a_start[s], ln = S.a_len[s];
-        for (int i = tid; i < ln; i += NT) { const int c = S.s1_cells[st + i]; hc[off + i] = c; hn[off + i] = cnode[c]; }
+        for (int i = tid; i < ln; i += NT) { const int c = s1_cells[st + i]; hc[off + i] = c; hn[off + i] = cnode[c]; }
         off += ln;
       }
       nb = off;
       cur_best = best;
+      ++epoch; xtop = ld;                      // every cross block belongs to the previous best area
       __syncthreads();
       extend_D(0, nb);
     }
-    if (tid == 0) sh_i[2] = 0;
+    if (tid == 0) sh_i[3] = 0;
     __syncthreads();
     TICK(4);                              // pick the largest area, materialise its lists / dense block
     // --- neighbouring areas in discovery order (:217-223): key = (position of X in V[best], dict key, dir)
@@ -521,11 +598,35 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         if (!wrapped && S.fin[kk]) continue;          // finalised cells are `unavail` (sentinel), :54-77
         const unsigned long long key = ((unsigned long long)p << 32) | ((unsigned long long)kk << 2) | (unsigned)d;
         const unsigned long long old = atomicMin(&S.okey[kk], key);
-        if (old == NOKEY64) S.nlist[atomicAdd(&sh_i[2], 1)] = kk;
+        if (old == NOKEY64) S.nlist[atomicAdd(&sh_i[3], 1)] = kk;
       }
     }
     __syncthreads();
-    const int nn = sh_i[2];
+    const int nn = sh_i[3];
+    // --- dense path bookkeeping: every neighbour gets a column range of D for its cross block and a range of
+    //     selfbuf for its own (best-independent) row means; if either does not fit the round uses the gather path
+    if (tid == 0) {
+      int ok = d_ok ? 1 : 0, top = xtop, stop = self_top;
+      for (int q = 0; q < nn && ok; ++q) {
+        const int kk = S.nlist[q], nk = S.size[kk];
+        if (S.xep[kk] != epoch) {
+          if (top - nk < nb) { ok = 0; break; }
+          top -= nk; S.xoff[kk] = top; S.xep[kk] = epoch; S.xrows[kk] = 0;
+        }
+        if (S.self_sz[kk] != nk && S.self_sz[kk] != -nk) {
+          if ((size_t)stop + nk > self_cap(C)) { ok = 0; break; }
+          S.self_off[kk] = stop; stop += nk; S.self_sz[kk] = -nk;     // allocated, not yet computed
+        }
+      }
+      sh_x[0] = top; sh_x[1] = ok; sh_x[2] = stop;
+      unsigned long long cons = 0;     // correlations the reference consumes this round: n(n-1)/2 per neighbour
+      for (int q = 0; q < nn; ++q) { const unsigned long long n = (unsigned long long)(nb + S.size[S.nlist[q]]); cons += n * (n - 1) / 2; }
+      wk += cons;
+    }
+    __syncthreads();
+    xtop = sh_x[0];
+    self_top = sh_x[2];
+    const bool dense = sh_x[1] != 0;
     TICK(5);                              // neighbour discovery
     // --- hypothetical merges (:224-253), neighbours processed in chunks that fit the row-mean buffer
     int q0 = 0;
@@ -538,33 +639,127 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         if (q1 > q0 && (rows + nb + sz > RM || cells + sz > (size_t)C)) break;
         rows += nb + sz; cells += sz; ++q1;
       }
-      // materialise the neighbours' node lists; sh_koff = node-list offsets, sh_uoff = row-unit offsets
+      const int nch = q1 - q0;
+      // materialise the neighbours' node lists; sh_koff = node-list offsets, sh_uoff = row-unit offsets (gather path),
+      // sh_goff / sh_soff = cross-block rows / self rows still to be filled (dense path)
       if (tid == 0) {
-        int off = 0, uo = 0;
+        int off = 0, uo = 0, go = 0, so = 0;
         for (int q = q0; q < q1; ++q) {
-          const int sz = S.size[S.nlist[q]];
-          sh_koff[q - q0] = off; sh_uoff[q - q0] = uo;
+          const int kk = S.nlist[q], sz = S.size[kk];
+          const int c = q - q0;
+          sh_koff[c] = off; sh_uoff[c] = uo; sh_goff[c] = go; sh_soff[c] = so;
           off += sz; uo += nb + sz;
+          if (dense) {
+            sh_xo[c] = S.xoff[kk]; sh_r0[c] = S.xrows[kk]; sh_so[c] = S.self_off[kk];
+            go += nb - S.xrows[kk];
+            if (S.self_sz[kk] != sz) so += sz;
+            S.xrows[kk] = nb;
+          }
         }
-        sh_koff[q1 - q0] = off; sh_uoff[q1 - q0] = uo;
+        sh_koff[nch] = off; sh_uoff[nch] = uo; sh_goff[nch] = go; sh_soff[nch] = so;
       }
       __syncthreads();
       for (int q = q0; q < q1; ++q) {
         int off = sh_koff[q - q0];
         for (int s = S.nlist[q]; s >= 0; s = S.seg_next[s]) {
           const int st = S.a_start[s], ln = S.a_len[s];
-          for (int i = tid; i < ln; i += NT) knl[off + i] = cnode[S.s1_cells[st + i]];
+          for (int i = tid; i < ln; i += NT) knl[off + i] = cnode[s1_cells[st + i]];
           off += ln;
         }
       }
       __syncthreads();
       TICK(6);                            // neighbour node lists
-      // row means r_p = nanmean(R[hyp_p, hyp_q], q > p): ONE THREAD per (neighbour, row), consecutive threads on
-      // consecutive rows so the best x best part streams coalesced from the diagonal-major dense block
-      {
-        const int nch = q1 - q0;
+      if (dense) {
+        // ---- (a) fill what is missing: cross-block rows [r0, nb) of every neighbour, one 8-lane group per row ...
+        const int G = sh_goff[nch];
+        for (int u = g; u < G; u += NG) {
+          int qc = 0;
+          while (u >= sh_goff[qc + 1]) ++qc;
+          const int p = sh_r0[qc] + (u - sh_goff[qc]);
+          const int nk = sh_koff[qc + 1] - sh_koff[qc];
+          const int32_t* kn = knl + sh_koff[qc];
+          const double* row = R + (size_t)hn[p] * ldn;
+          double* dst = D + (size_t)p * ld + sh_xo[qc];
+          for (int qq = 0; qq < nk; qq += 64) {
+            double v[8];
+#pragma unroll
+            for (int u2 = 0; u2 < 8; ++u2) v[u2] = __ldg(row + kn[min(qq + 8 * u2 + j, nk - 1)]);
+            sie_fence_regs<8>(v);
+#pragma unroll
+            for (int u2 = 0; u2 < 8; ++u2) { const int q = qq + 8 * u2 + j; if (q < nk) dst[q] = v[u2]; }
+          }
+        }
+        // ---- ... and the neighbours' own row means r_{nb+p'} = nanmean(R[k_p', k_q'], q' > p'), which do not depend
+        //      on the best area: computed once per area, reused every round it is a neighbour
+        const int SU = sh_soff[nch];
+        for (int u = g; u < SU; u += NG) {
+          int qc = 0;
+          while (u >= sh_soff[qc + 1]) ++qc;
+          const int pp = u - sh_soff[qc];
+          const int nk = sh_koff[qc + 1] - sh_koff[qc];
+          const int32_t* kn = knl + sh_koff[qc];
+          const int len = nk - 1 - pp;
+          int nanc = 0;
+          double sum = 0.0;
+          if (len > 0) {
+            const double* row = R + (size_t)kn[pp] * ldn;
+            const int32_t* kq = kn + pp + 1;
+            sum = sie_pw_sum8<MAXD>([&](int i) { return __ldg(row + kq[i]); }, len, j, gmask, nanc);
+            nanc += __shfl_xor_sync(gmask, nanc, 1);
+            nanc += __shfl_xor_sync(gmask, nanc, 2);
+            nanc += __shfl_xor_sync(gmask, nanc, 4);
+          }
+          if (j == 0) selfbuf[sh_so[qc] + pp] = (len - nanc > 0) ? sum / (double)(len - nanc) : sie_nan();   // nanmean([]) = nan
+        }
+        __syncthreads();
+        if (tid == 0) for (int q = q0; q < q1; ++q) { const int kk = S.nlist[q]; S.self_sz[kk] = S.size[kk]; }
+        TICK(9);                          // cross blocks + self row means (first sight of a neighbour)
+        // ---- (b) row means of the best rows: r_p = nanmean(D[p][p+1..nb) ++ D[p][xoff..xoff+nk)), two contiguous runs
+        const int total = nch * nb;
+        for (int u = g; u < total; u += NG) {
+          const int qc = u / nb;
+          const int p = u - qc * nb;
+          const int nk = sh_koff[qc + 1] - sh_koff[qc];
+          const int nbb = nb - 1 - p;
+          const int len = nbb + nk;
+          const double* base1 = D + (size_t)p * ld + (p + 1);
+          const int gap = sh_xo[qc] - nb;           // element i >= nbb lives at base1[i + gap]
+          int nanc = 0;
+          const double sum = sie_pw_tree<MAXD>([&](int lo, int ln) -> double {
+            if (lo + ln <= nbb || lo >= nbb) {
+              const double r = sie_pw_leaf8_contig(base1 + lo + j + (lo >= nbb ? gap : 0), ln, j, gmask);
+              if (r == r) return r;
+            }
+            return sie_pw_leaf8([&](int i) { return base1[i + (i >= nbb ? gap : 0)]; }, lo, ln, j, gmask, nanc);
+          }, len);
+          nanc += __shfl_xor_sync(gmask, nanc, 1);
+          nanc += __shfl_xor_sync(gmask, nanc, 2);
+          nanc += __shfl_xor_sync(gmask, nanc, 4);
+          if (j == 0) rowmean[u] = (len - nanc > 0) ? sum / (double)(len - nanc) : sie_nan();
+        }
+        __syncthreads();
+        TICK(7);                          // row means of the hypothetical areas
+        // ---- (c) stat_k = nanmean(r_0..r_{n-1})  (:253): best rows from rowmean, the neighbour's own from selfbuf
+        for (int q = q0 + g; q < q1; q += NG) {
+          const int qc = q - q0;
+          const int nk = sh_koff[qc + 1] - sh_koff[qc];
+          const int n = nb + nk;
+          const double* rm = rowmean + (size_t)qc * nb;
+          const double* sf = selfbuf + sh_so[qc] - nb;
+          int nanc = 0;
+          const double sum = sie_pw_sum8<MAXD>([&](int i) { const double* q2 = (i < nb) ? rm + i : sf + i; return *q2; }, n, j, gmask, nanc);
+          nanc += __shfl_xor_sync(gmask, nanc, 1);
+          nanc += __shfl_xor_sync(gmask, nanc, 2);
+          nanc += __shfl_xor_sync(gmask, nanc, 4);
+          if (j == 0) S.stat[S.nlist[q]] = (n - nanc > 0) ? sum / (double)(n - nanc) : sie_nan();
+        }
+        __syncthreads();
+        TICK(8);                          // statistic per neighbour
+      } else {
+        // ---- gather path (best area or neighbours too large for the dense block): one 8-lane group per
+        //      (neighbour, row), everything gathered from R
         const int total = sh_uoff[nch];
-        for (int u = tid; u < total; u += NT) {
+        for (int u = g; u < total; u += NG) {
           int qc = 0;
           while (u >= sh_uoff[qc + 1]) ++qc;
           const int p = u - sh_uoff[qc];
@@ -575,66 +770,60 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
           int nanc = 0;
           double sum = 0.0;
           if (len > 0) {
-            wk += (unsigned long long)len;
             if (p < nb) {
               const double* row = R + (size_t)hn[p] * ldn;
               const int nbb = nb - 1 - p;              // elements of the row inside the best area
-              if (d_ok) {
-                const double* dcol = D + p;
-                sum = sie_pw_sum_thread(
-                    [&](int i) { return (i < nbb) ? dcol[(size_t)i * dcap] : __ldg(row + kn[i - nbb]); }, len, nanc);
-              } else {
-                sum = sie_pw_sum_thread(
-                    [&](int i) { return __ldg(row + ((i < nbb) ? hn[p + 1 + i] : kn[i - nbb])); }, len, nanc);
-              }
+              sum = sie_pw_sum8<MAXD>([&](int i) { const int32_t* q = (i < nbb) ? hn + (p + 1 + i) : kn + max(i - nbb, 0); return __ldg(row + *q); }, len, j, gmask, nanc);
             } else {
               const double* row = R + (size_t)kn[p - nb] * ldn;
               const int32_t* kq = kn + (p - nb) + 1;
-              sum = sie_pw_sum_thread([&](int i) { return __ldg(row + kq[i]); }, len, nanc);
+              sum = sie_pw_sum8<MAXD>([&](int i) { return __ldg(row + kq[i]); }, len, j, gmask, nanc);
             }
+            nanc += __shfl_xor_sync(gmask, nanc, 1);
+            nanc += __shfl_xor_sync(gmask, nanc, 2);
+            nanc += __shfl_xor_sync(gmask, nanc, 4);
           }
-          S.rowmean[u] = (len - nanc > 0) ? sum / (double)(len - nanc) : sie_nan();   // nanmean([]) = nan
+          if (j == 0) rowmean[u] = (len - nanc > 0) ? sum / (double)(len - nanc) : sie_nan();   // nanmean([]) = nan
         }
+        __syncthreads();
+        TICK(7);                          // row means of the hypothetical areas
+        // stat_k = nanmean(r_0..r_{n-1})  (:253) -- one 8-lane group per neighbour
+        for (int q = q0 + g; q < q1; q += NG) {
+          const int n = sh_uoff[q - q0 + 1] - sh_uoff[q - q0];
+          const double* rm = rowmean + sh_uoff[q - q0];
+          int nanc = 0;
+          const double sum = sie_pw_sum8<MAXD>([&](int i) { return rm[i]; }, n, j, gmask, nanc);
+          nanc += __shfl_xor_sync(gmask, nanc, 1);
+          nanc += __shfl_xor_sync(gmask, nanc, 2);
+          nanc += __shfl_xor_sync(gmask, nanc, 4);
+          if (j == 0) S.stat[S.nlist[q]] = (n - nanc > 0) ? sum / (double)(n - nanc) : sie_nan();
+        }
+        __syncthreads();
+        TICK(8);                          // statistic per neighbour
       }
-      __syncthreads();
-      TICK(7);                            // row means of the hypothetical areas
-      // stat_k = nanmean(r_0..r_{n-1})  (:253) -- one 8-lane group per neighbour
-      for (int q = q0 + g; q < q1; q += NG) {
-        const int n = sh_uoff[q - q0 + 1] - sh_uoff[q - q0];
-        const double* rm = S.rowmean + sh_uoff[q - q0];
-        int nanc = 0;
-        const double sum = sie_pw_sum8([&](int i) { return rm[i]; }, n, j, gmask, nanc);
-        nanc += __shfl_xor_sync(gmask, nanc, 1);
-        nanc += __shfl_xor_sync(gmask, nanc, 2);
-        nanc += __shfl_xor_sync(gmask, nanc, 4);
-        if (j == 0) S.stat[S.nlist[q]] = (n - nanc > 0) ? sum / (double)(n - nanc) : sie_nan();
-      }
-      __syncthreads();
-      TICK(8);                            // statistic per neighbour
       q0 = q1;
     }
     // --- max(Anei_Rs.items(), key=itemgetter(1)) (:255): first in discovery order wins ties; a NaN in
     //     first position is never displaced (list comparison semantics)
-    Pick loc2 = pick_none(), f1 = pick_none();
+    Rec loc2 = rec_none(), f1 = rec_none();
     for (int q = tid; q < nn; q += NT) {
       const int kk = S.nlist[q];
       const double st = S.stat[kk];
       const unsigned long long ok = S.okey[kk];
-      Pick c1; c1.hi = 1ull; c1.lo = ~ok;               // first discovered neighbour = smallest discovery key
-      f1 = pick_max(f1, c1);
+      Rec c1; c1.ord = 1ull; c1.pri = ~ok; c1.a = (uint32_t)kk; c1.b = 0u;   // first discovered = smallest discovery key
+      f1 = rec_max(f1, c1);
       if (st == st) {
-        Pick cur; cur.hi = ord_of(st); cur.lo = ~ok;
-        loc2 = pick_max(loc2, cur);
+        Rec cur; cur.ord = ord_of(st); cur.pri = ~ok; cur.a = (uint32_t)kk; cur.b = 0u;
+        loc2 = rec_max(loc2, cur);
       }
     }
-    const Pick firstn = block_pick(f1, slots);
-    const Pick win = block_pick(loc2, slots);
+    const Rec firstn = block_arg<2>(f1, rslots, par);
+    const Rec win = block_arg<2>(loc2, rslots, par);
     bool merge = false;
     int kk = -1;
-    if (nn > 0 && win.hi != 0ull) {
-      const int first_idx = (int)((~firstn.lo >> 2) & 0x3fffffffull);
-      const double first_stat = S.stat[first_idx];
-      if (first_stat == first_stat && ord_to_double(win.hi) > tau) { merge = true; kk = (int)((~win.lo >> 2) & 0x3fffffffull); }
+    if (nn > 0 && win.ord != 0ull) {
+      const double first_stat = S.stat[(int)firstn.a];
+      if (first_stat == first_stat && ord_to_double(win.ord) > tau) { merge = true; kk = (int)win.a; }
     }
     __syncthreads();
     // reset discovery keys
@@ -645,7 +834,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
       for (int s = kk; s >= 0; s = S.seg_next[s]) {
         const int st = S.a_start[s], ln = S.a_len[s];
         for (int i = tid; i < ln; i += NT) {
-          const int c = S.s1_cells[st + i];
+          const int c = s1_cells[st + i];
           hc[off + i] = c; hn[off + i] = cnode[c]; lab[c] = best;
         }
         off += ln;
@@ -657,13 +846,14 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         S.size[best] += S.size[kk];
         S.size[kk] = 0;
       }
+      if (off > xtop) { ++epoch; xtop = ld; }  // the best columns would run into the cross blocks: drop them
       extend_D(nb, off);
       nb = off;
     } else {
       if (tid == 0) S.fin[best] = 1;           // :262-265 all cells of V[best] become unavailable
     }
     __syncthreads();
-    TICK(9);                              // winner, merge / finalise, dense block extension
+    TICK(12);                             // winner, merge / finalise, dense block extension
   }
 
   // =============================================================== output in dict order (ascending key)
@@ -676,8 +866,12 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
     work_all[SIE_AREA_WORK * b + 2] = (unsigned long long)(clk2 - clk1);    // SM cycles in step 2
     work_all[SIE_AREA_WORK * b + 3] = (n_steps << 32) | n_rounds;           // growth steps, merge rounds
     for (int i = 0; i < 11; ++i) work_all[SIE_AREA_WORK * b + 4 + i] = ph[i];
-    work_all[SIE_AREA_WORK * b + 15] = ph[11];
+    work_all[SIE_AREA_WORK * b + 24] = ph[11];
+    work_all[SIE_AREA_WORK * b + 25] = ph[12];
+    work_all[SIE_AREA_WORK * b + 15] = n_slow;
   }
+  if (tid == BKW * 32 && work_all)
+    for (int i = 0; i < 8; ++i) work_all[SIE_AREA_WORK * b + 16 + i] = bph[i];
   if (tid == 0) {
     int cnt = 0, off = 0;
     for (int k = 0; k < nA; ++k) {
@@ -692,16 +886,16 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
     out_start[cnt] = off;
     n_areas_all[b] = cnt;
     status_all[b] = (cnt < 2) ? SIE_JOB_FEW_AREAS : SIE_JOB_OK;   // :212 / :278 ValueError
-    sh_i[3] = cnt;
+    sh_i[4] = cnt;
   }
   __syncthreads();
-  const int cnt = sh_i[3];
+  const int cnt = sh_i[4];
   for (int a = 0; a < cnt; ++a) {
     int off = out_start[a];
     for (int s = S.nlist[a]; s >= 0; s = S.seg_next[s]) {
       const int st = S.a_start[s], ln = S.a_len[s];
       for (int i = tid; i < ln; i += NT) {
-        const int c = S.s1_cells[st + i];
+        const int c = s1_cells[st + i];
         out_cells[off + i] = c;
         out_label[c] = a;
       }
@@ -728,22 +922,29 @@ extern "C" int sie_area_level(const double* R, const double* stencil, const int3
   SIE_CHECK_ARG(B > 0 && X > 0 && Y > 0 && ldn > 0 && max_areas > 0, "non-positive size");
   const int C = X * Y;
   SIE_CHECK_ARG(max_areas <= C / 2 + 1, "max_areas cannot exceed C/2+1");
-  SIE_CHECK_ARG((long long)C < (1ll << 28), "grid too large for the frontier key encoding");
+  SIE_CHECK_ARG((long long)C < (1ll << 22), "grid too large (frontier key encoding / pairwise tree depth)");
   const size_t per_job = scratch_per_job(C, max_areas);
   SIE_CHECK_ARG(scratch_bytes >= per_job * (size_t)B, "scratch too small");
   int dev = 0, max_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const size_t slot_bytes = sizeof(double) * 16 * FCAP + sizeof(int32_t) * FCAP;
-  // shared-memory tiers: 2 = all seven integer arrays, 1 = six (neighbour lists stay in global), 0 = slot state only
-  size_t smem = slot_bytes + sizeof(int32_t) * (size_t)7 * C;
-  int use_smem = 2;
-  if (smem + 4096 > (size_t)max_optin) { smem = slot_bytes + sizeof(int32_t) * (size_t)6 * C; use_smem = 1; }
-  if (smem + 4096 > (size_t)max_optin) { smem = slot_bytes; use_smem = 0; }
-  cudaFuncSetAttribute(k_area_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_area_level<<<B, NT, smem, (cudaStream_t)stream>>>(
+  // Shared-memory placement: slot state always on chip; then evict arrays to global scratch, least
+  // latency-critical first, until the rest fits.
+  const size_t budget = (size_t)max_optin - 4096;    // static shared memory + alignment slack
+  const size_t ibytes = align_up(sizeof(int32_t) * (size_t)C, 16);
+  size_t smem = align_up(slot_bytes(), 16) + 64 + area_tab_bytes(max_areas) + 7 * ibytes;
+  int place = 0;
+  const int order[8] = {PL_KNL, PL_AREA, PL_HC, PL_FLIST, PL_HN, PL_FKEY, PL_CNL, PL_LAB};
+  for (int i = 0; i < 8 && smem > budget; ++i) {
+    place |= order[i];
+    smem -= (order[i] == PL_AREA) ? area_tab_bytes(max_areas) : ibytes;
+  }
+  SIE_CHECK_ARG(smem <= budget, "shared memory budget");
+  auto kern = (place == 0 && C < 8192) ? k_area_level<true> : k_area_level<false>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<B, NT, smem, (cudaStream_t)stream>>>(
       R, stencil, node_cell, cell_node, n_nodes, tau, first_nan_cell, X, Y, ldn, latlon, max_areas, area_cells,
-      area_start, area_key, n_areas, label, status, (unsigned char*)scratch, per_job, use_smem,
+      area_start, area_key, n_areas, label, status, (unsigned char*)scratch, per_job, place,
       (unsigned long long*)work);
   SIE_CHECK_LAUNCH();
   return SIE_OK;

@@ -40,6 +40,58 @@ __device__ __forceinline__ double sie_nan() { return __longlong_as_double(0x7ff8
 // sequence whose i-th element is get(i); NaN entries count as 0 and are tallied in `nan_cnt` (nanmean; the
 // per-lane tallies must be summed over the group by the caller).  All 8 lanes return the same value.
 // -------------------------------------------------------------------------------------------------
+// Compiler fence over a register array: everything that defines v[] (the gathers) is ordered before, everything
+// that consumes it (the adds) after, so a leaf's gathers are all in flight before the first add instead of being
+// interleaved load-use-load-use (which serialises the memory round trips).
+template <int NQ> __device__ __forceinline__ void sie_fence_regs(double (&v)[NQ]);
+template <> __device__ __forceinline__ void sie_fence_regs<1>(double (&v)[1]) { asm volatile("" : "+d"(v[0])); }
+template <> __device__ __forceinline__ void sie_fence_regs<4>(double (&v)[4]) {
+  asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]));
+}
+template <> __device__ __forceinline__ void sie_fence_regs<8>(double (&v)[8]) {
+  asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]), "+d"(v[5]), "+d"(v[6]), "+d"(v[7]));
+}
+template <> __device__ __forceinline__ void sie_fence_regs<16>(double (&v)[16]) {
+  asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]), "+d"(v[5]), "+d"(v[6]), "+d"(v[7]),
+                    "+d"(v[8]), "+d"(v[9]), "+d"(v[10]), "+d"(v[11]), "+d"(v[12]), "+d"(v[13]), "+d"(v[14]), "+d"(v[15]));
+}
+
+// Lane j's part of one leaf: accumulator j over the `ngrp` full groups of 8 (sequential, numpy's order) and tail
+// element j.  The NQ + 1 gathers are unconditional (indices clamped to the last element; the extras are masked
+// out of the sums) so they are issued back to back.  get(i) must be valid for lo <= i < lo + n.
+template <int NQ, typename Get>
+__device__ __forceinline__ void sie_pw_lane8(Get get, int lo, int n, int ngrp, int ntail, int j, double& acc, double& tv,
+                                             int& nan_cnt) {
+  double v[NQ];
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) v[k] = get(lo + min(8 * k + j, n - 1));
+  double t[1];
+  t[0] = get(lo + min(8 * ngrp + j, n - 1));
+  sie_fence_regs<NQ>(v);
+  sie_fence_regs<1>(t);
+  tv = t[0];
+  if (j >= ntail) tv = 0.0;
+  if (tv != tv) { tv = 0.0; ++nan_cnt; }
+  double r = 0.0;
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) {
+    if (k < ngrp) {
+      double x = v[k];
+      if (x != x) { x = 0.0; ++nan_cnt; }
+      r = (k == 0) ? x : __dadd_rn(r, x);
+    }
+  }
+  acc = r;
+}
+template <typename Get>
+__device__ __forceinline__ void sie_pw_lane8_any(Get get, int lo, int n, int ngrp, int ntail, int j, double& acc,
+                                                 double& tv, int& nan_cnt) {
+  if (ngrp <= 1) sie_pw_lane8<1>(get, lo, n, ngrp, ntail, j, acc, tv, nan_cnt);
+  else if (ngrp <= 4) sie_pw_lane8<4>(get, lo, n, ngrp, ntail, j, acc, tv, nan_cnt);
+  else if (ngrp <= 8) sie_pw_lane8<8>(get, lo, n, ngrp, ntail, j, acc, tv, nan_cnt);
+  else sie_pw_lane8<16>(get, lo, n, ngrp, ntail, j, acc, tv, nan_cnt);
+}
+
 template <typename Get>
 __device__ __forceinline__ double sie_pw_leaf8(Get get, int lo, int n, int j, unsigned gmask, int& nan_cnt) {
   // All gathers of the leaf (<= 16 per lane + one tail element) are issued before the first add, so a leaf costs
@@ -47,25 +99,10 @@ __device__ __forceinline__ double sie_pw_leaf8(Get get, int lo, int n, int j, un
   const int nfull = (n < 8) ? 0 : n - (n & 7);
   const int ngrp = nfull >> 3;                       // <= 16 full groups of 8
   const int ntail = n - nfull;                       // < 8 (or all of a short list)
-  double v[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) v[k] = (k < ngrp) ? get(lo + 8 * k + j) : 0.0;
-  double tv = (j < ntail) ? get(lo + nfull + j) : 0.0;
-  if (tv != tv) { tv = 0.0; ++nan_cnt; }
-  double res;
-  if (ngrp == 0) {
-    res = 0.0;                                       // n < 8: left-to-right from 0.0
-  } else {
-    double r = v[0];
-    if (r != r) { r = 0.0; ++nan_cnt; }
-#pragma unroll
-    for (int k = 1; k < 16; ++k) {
-      if (k < ngrp) {
-        double x = v[k];
-        if (x != x) { x = 0.0; ++nan_cnt; }
-        r = __dadd_rn(r, x);
-      }
-    }
+  double r, tv;
+  sie_pw_lane8_any(get, lo, n, ngrp, ntail, j, r, tv, nan_cnt);
+  double res = 0.0;                                  // n < 8: left-to-right from 0.0
+  if (ngrp > 0) {
     // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) : xor-butterfly inside the 8-lane group (IEEE add commutes)
     r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));
     r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));
@@ -76,108 +113,80 @@ __device__ __forceinline__ double sie_pw_leaf8(Get get, int lo, int n, int j, un
   return res;
 }
 
-// Full pairwise sum of a sequence of length n by one 8-lane group; leaves are visited left to right and
-// combined along the recursion tree with an explicit stack (depth <= 24 covers n < 2^31).
-template <typename Get>
-__device__ __forceinline__ double sie_pw_sum8(Get get, int n, int j, unsigned gmask, int& nan_cnt) {
-  if (n <= 128) return sie_pw_leaf8(get, 0, n, j, gmask, nan_cnt);
-  // iterative post-order walk of pairwise(lo,n) = pairwise(lo,n2) + pairwise(lo+n2,n-n2)
-  int st_lo[24], st_n[24];
-  double st_val[24];
-  unsigned char st_state[24];
-  int sp = 0;
-  st_lo[0] = 0; st_n[0] = n; st_state[0] = 0; sp = 1;
-  double ret = 0.0;
-  while (sp > 0) {
-    int t = sp - 1;
-    if (st_state[t] == 0) {
-      if (st_n[t] <= 128) {
-        ret = sie_pw_leaf8(get, st_lo[t], st_n[t], j, gmask, nan_cnt);
-        --sp;
-      } else {
-        int n2 = st_n[t] / 2; n2 -= n2 % 8;
-        st_state[t] = 1;
-        st_lo[sp] = st_lo[t]; st_n[sp] = n2; st_state[sp] = 0; ++sp;
-      }
-    } else if (st_state[t] == 1) {
-      st_val[t] = ret;
-      int n2 = st_n[t] / 2; n2 -= n2 % 8;
-      st_state[t] = 2;
-      st_lo[sp] = st_lo[t] + n2; st_n[sp] = st_n[t] - n2; st_state[sp] = 0; ++sp;
-    } else {
-      ret = __dadd_rn(st_val[t], ret);
-      --sp;
-    }
-  }
-  return ret;
-}
-
-// One THREAD sums a whole sequence in numpy's pairwise order: the 8 accumulators of a leaf live in registers, so a
-// warp evaluates 32 independent sequences at once (used where many rows are summed side by side and consecutive
-// threads read consecutive addresses).  Bit-identical to sie_pw_sum8 / np.sum.
-template <typename Get>
-__device__ __forceinline__ double sie_pw_leaf_thread(Get get, int lo, int n, int& nan_cnt) {
-  auto val = [&](int i) {
-    double x = get(i);
-    if (x != x) { x = 0.0; ++nan_cnt; }
-    return x;
-  };
-  if (n < 8) {
-    double res = 0.0;
-    for (int i = 0; i < n; ++i) res = __dadd_rn(res, val(lo + i));
-    return res;
-  }
-  double r[8];
+// One leaf (n <= 128) whose elements are CONTIGUOUS in memory: q = address of element `lo + j` (lane j).  Loads use
+// immediate offsets (no index arithmetic), NaN is not screened: a NaN element makes the result NaN and the caller
+// redoes the leaf with the screening path.  Reads up to 135 elements past q[0] (masked out of the sum): the
+// caller guarantees that memory is readable.
+template <int NQ>
+__device__ __forceinline__ double sie_pw_leaf8_contig_n(const double* q, int ngrp, int nt, int j, unsigned gmask) {
+  double v[NQ];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) r[q] = val(lo + q);
-  const int nfull = n - (n & 7);
-#pragma unroll 2
-  for (int i = 8; i < nfull; i += 8) {
-    double x[8];
+  for (int k = 0; k < NQ; ++k) v[k] = q[8 * k];
+  double t[1];
+  t[0] = q[8 * ngrp];
+  sie_fence_regs<NQ>(v);
+  sie_fence_regs<1>(t);
+  double r = v[0];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) x[q] = get(lo + i + q);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      double y = x[q];
-      if (y != y) { y = 0.0; ++nan_cnt; }
-      r[q] = __dadd_rn(r[q], y);
-    }
+  for (int k = 1; k < NQ; ++k) if (k < ngrp) r = __dadd_rn(r, v[k]);
+  double res = 0.0;
+  if (ngrp > 0) {
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+    res = r;
   }
-  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-  for (int i = nfull; i < n; ++i) res = __dadd_rn(res, val(lo + i));
+  const double tv = (j < nt) ? t[0] : 0.0;
+  for (int i = 0; i < nt; ++i) res = __dadd_rn(res, __shfl_sync(gmask, tv, i, 8));
   return res;
 }
+__device__ __forceinline__ double sie_pw_leaf8_contig(const double* q, int n, int j, unsigned gmask) {
+  const int ngrp = (n < 8) ? 0 : (n >> 3), nt = n - 8 * ngrp;
+  if (ngrp <= 1) return sie_pw_leaf8_contig_n<1>(q, ngrp, nt, j, gmask);
+  if (ngrp <= 4) return sie_pw_leaf8_contig_n<4>(q, ngrp, nt, j, gmask);
+  if (ngrp <= 8) return sie_pw_leaf8_contig_n<8>(q, ngrp, nt, j, gmask);
+  return sie_pw_leaf8_contig_n<16>(q, ngrp, nt, j, gmask);
+}
 
-template <typename Get>
-__device__ __forceinline__ double sie_pw_sum_thread(Get get, int n, int& nan_cnt) {
-  if (n <= 128) return sie_pw_leaf_thread(get, 0, n, nan_cnt);
-  int st_lo[24], st_n[24];
-  double st_val[24];
-  unsigned char st_state[24];
-  int sp = 1;
-  st_lo[0] = 0; st_n[0] = n; st_state[0] = 0;
-  double ret = 0.0;
-  while (sp > 0) {
-    const int t = sp - 1;
-    if (st_state[t] == 0) {
-      if (st_n[t] <= 128) {
-        ret = sie_pw_leaf_thread(get, st_lo[t], st_n[t], nan_cnt);
-        --sp;
-      } else {
-        int n2 = st_n[t] / 2; n2 -= n2 % 8;
-        st_state[t] = 1;
-        st_lo[sp] = st_lo[t]; st_n[sp] = n2; st_state[sp] = 0; ++sp;
-      }
-    } else if (st_state[t] == 1) {
-      st_val[t] = ret;
-      int n2 = st_n[t] / 2; n2 -= n2 % 8;
-      st_state[t] = 2;
-      st_lo[sp] = st_lo[t] + n2; st_n[sp] = st_n[t] - n2; st_state[sp] = 0; ++sp;
-    } else {
-      ret = __dadd_rn(st_val[t], ret);
-      --sp;
+// numpy's pairwise recursion pairwise(lo,n) = pairwise(lo,n2) + pairwise(lo+n2,n-n2), n2 = n/2 - (n/2)%8, over leaves of
+// <= 128 elements, walked left to right without a memory stack: the path from the root is a bit mask (bit d = "right
+// child at depth d+1"), node bounds are recomputed from the root (<= 16 integer steps), and the pending left-sibling
+// sums live in registers.  leaf(lo, len) returns the leaf's sum (uniform over the 8-lane group).  n < 2^22.
+// MAXD = tree depth supported: n <= 128 * 2^MAXD.
+template <int MAXD, typename Leaf>
+__device__ __forceinline__ double sie_pw_tree(Leaf leaf, int n) {
+  if (n <= 128) return leaf(0, n);
+  double val[MAXD];
+  unsigned path = 0u;
+  int depth = 0, lo = 0, len = n;
+  while (len > 128) { int n2 = len / 2; n2 -= n2 % 8; len = n2; ++depth; }
+  double ret;
+  while (true) {
+    ret = leaf(lo, len);
+    while (depth > 0 && ((path >> (depth - 1)) & 1u)) {          // finished a right child: add the left sibling
+      double left = 0.0;
+#pragma unroll
+      for (int d = 0; d < MAXD; ++d) if (d == depth - 1) left = val[d];
+      ret = __dadd_rn(left, ret);
+      path &= ~(1u << (depth - 1));
+      --depth;
     }
+    if (depth == 0) break;
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) if (d == depth - 1) val[d] = ret;   // finished a left child
+    path |= 1u << (depth - 1);
+    lo = 0; len = n;
+    for (int d = 0; d < depth; ++d) {
+      int n2 = len / 2; n2 -= n2 % 8;
+      if ((path >> d) & 1u) { lo += n2; len -= n2; } else { len = n2; }
+    }
+    while (len > 128) { int n2 = len / 2; n2 -= n2 % 8; len = n2; ++depth; }
   }
   return ret;
+}
+
+// Full pairwise sum of a sequence of length n by one 8-lane group (generic element getter).
+template <int MAXD = 16, typename Get>
+__device__ __forceinline__ double sie_pw_sum8(Get get, int n, int j, unsigned gmask, int& nan_cnt) {
+  return sie_pw_tree<MAXD>([&](int lo, int len) { return sie_pw_leaf8(get, lo, len, j, gmask, nan_cnt); }, n);
 }

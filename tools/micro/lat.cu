@@ -2,7 +2,11 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #define NT 512
-__global__ void probe(double* out, long long* cyc, const double* gsrc, int n) {
+__global__ void fill(double* p, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    p[i] = (double)((i * 2654435761ull + 12345ull) % n);
+}
+__global__ void probe(double* out, long long* cyc, const double* gsrc, int n, const double* big, size_t nbig) {
   __shared__ double sh[4096];
   __shared__ unsigned long long slots[32];
   const int tid = threadIdx.x;
@@ -80,6 +84,15 @@ __global__ void probe(double* out, long long* cyc, const double* gsrc, int n) {
     __syncthreads();
   }
   t1 = clock64(); if (tid == 0) cyc[8] = t1 - t0;
+  // 9: dependent DRAM gather chain (16) over a huge array (big = 4 GB), one thread per warp distinct lines
+  {
+    size_t gj = (size_t)tid * 1000003ull + blockIdx.x * 7777777ull;
+    t0 = clock64();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) gj = (size_t)__ldg(big + (gj % nbig)) + tid * 131ull;
+    t1 = clock64(); if (tid == 0) cyc[9] = t1 - t0;
+    gi += (int)gj;
+  }
   out[tid] = acc + (double)u + idx + gi;
 }
 int main() {
@@ -89,12 +102,15 @@ int main() {
   cudaMalloc(&g, n * 8);
   double* h = new double[n]; for (int i = 0; i < n; ++i) h[i] = (double)((i * 7919LL + 13) % n);
   cudaMemcpy(g, h, n * 8, cudaMemcpyHostToDevice);
+  const size_t nbig = (size_t)1 << 29;   // 4 GB
+  double* big; cudaMalloc(&big, nbig * 8);
+  fill<<<4096, 256>>>(big, nbig);
   cudaMalloc(&cyc, 16 * 8); cudaMemset(cyc, 0, 128);
-  for (int it = 0; it < 2; ++it) probe<<<1, NT>>>(out, cyc, g, n);
+  for (int it = 0; it < 2; ++it) probe<<<1, NT>>>(out, cyc, g, n, big, nbig);
   cudaDeviceSynchronize();
   long long hc[16]; cudaMemcpy(hc, cyc, 128, cudaMemcpyDeviceToHost);
-  const char* names[] = {"dadd chain x64", "dadd 8acc x64 (512 thr)", "ddiv chain x16", "shfl64+sel chain x32", "syncthreads x16", "smem dep chain x32", "global L2 gather chain x16", "i2d+dsetp chain x32", "block argmax x8"};
-  for (int i = 0; i < 9; ++i) printf("%-28s %8lld cycles\n", names[i], hc[i]);
+  const char* names[] = {"dadd chain x64", "dadd 8acc x64 (512 thr)", "ddiv chain x16", "shfl64+sel chain x32", "syncthreads x16", "smem dep chain x32", "global L2 gather chain x16", "i2d+dsetp chain x32", "block argmax x8", "DRAM gather chain x16 (512 thr)"};
+  for (int i = 0; i < 10; ++i) printf("%-28s %8lld cycles\n", names[i], hc[i]);
   printf("err %s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }

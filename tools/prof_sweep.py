@@ -15,9 +15,10 @@ for tag,eng,T in (('sic',sw.sic,sw.plan.job_T),('sst',sw.sst,sw.plan.sst_T)):
     for b in list(order[:8])+list(order[-3:]):
         print(tag,b,T[b],nn[b],na[b],wk[b,0],round(wk[b,1]/1e6,2),round(wk[b,2]/1e6,2),wk[b,3]>>32,wk[b,3]&0xffffffff)
     print(tag,'sum step1 Mcyc',wk[:,1].sum()/1e6,'sum step2',wk[:,2].sum()/1e6)
-    names=['seed','argmax','update','gather','s2.select','s2.discover','s2.lists','s2.rowmeans','s2.stat','s2.merge','eval','pre-eval']
+    names=['seed','argmax','create','update+gather','s2.select','s2.discover','s2.lists','s2.rowmeans','s2.stat','s2.fill','eval','slow-steps']
     for b in list(order[:3])+list(order[-2:]):
         print(tag,b,'phases Mcyc',{n:round(wk[b,4+i]/1e6,2) for i,n in enumerate(names)})
+        print(tag,b,'BK Mcyc outside/detect/assign/init/tail',[round(wk[b,16+i]/1e6,2) for i in range(5)],'inits',wk[b,21],'owner-wait',round(wk[b,24]/1e6,2),'s2.merge',round(wk[b,25]/1e6,2),'slow',wk[b,15])
 raw=sw.raw
 order=np.argsort(-raw['cycles_total'])
 print('gp: idx meta n npred m s info total_Mcyc expm_Mcyc')
