@@ -119,6 +119,18 @@ __device__ __forceinline__ Rec warp_arg(const Rec& r) {
   const uint32_t w2 = (uint32_t)(r.pri >> 32), w3 = (uint32_t)r.pri;
   const uint32_t m0 = __reduce_max_sync(FULL, w0);
   bool ok = (w0 == m0);
+  {   // common case: the high word alone decides (one lane holds the maximum) -> one redux + one ballot
+    const unsigned b0 = __ballot_sync(FULL, ok);
+    if ((b0 & (b0 - 1u)) == 0u) {
+      const int src0 = __ffs(b0) - 1;
+      Rec o;
+      o.ord = ((unsigned long long)m0 << 32) | __shfl_sync(FULL, w1, src0);
+      o.pri = ((unsigned long long)__shfl_sync(FULL, w2, src0) << 32) | __shfl_sync(FULL, w3, src0);
+      o.a = __shfl_sync(FULL, r.a, src0);
+      o.b = __shfl_sync(FULL, r.b, src0);
+      return o;
+    }
+  }
   const uint32_t m1 = __reduce_max_sync(FULL, ok ? w1 : 0u);
   ok = ok && (w1 == m1);
   const uint32_t m2 = __reduce_max_sync(FULL, ok ? w2 : 0u);
