@@ -245,24 +245,32 @@ class SweepPlan:
         (June1st_retro.py:284-290, rounded to 3 d.p.), the un-rounded values under '<region>_raw_*'.
         `raw`/`meta` may be the concatenation over all ranks (after a gather)."""
         meta = self.prob_meta if meta is None else meta
+        raw = np.asarray(raw)
+        m = np.asarray(meta, dtype=np.int64).reshape(-1, 3)
         out = {}
-        for (ci, k, year), r in zip(meta, raw):
-            cfg = self.cfgs[ci]
-            g = out.setdefault(cfg.name, {})
-            reg = cfg.regions[k]
-            for key in ("_fmean", "_fvar", "_fmean_rt", "_raw_fmean", "_raw_fvar", "_raw_fmean_rt"):
-                g.setdefault(reg + key, np.full(len(self.years), np.nan))
-            i = year - self.fmin
-            fmean = np.round(r["fmean"], 3)
-            row = year - (self.fmin - 1) - 1
-            slope, icpt = self.sie_trend[reg][row]
-            lineT = (np.arange(year - FIRST_YEAR + 1) * slope) + icpt
-            g[reg + "_fmean"][i] = fmean
-            g[reg + "_fvar"][i] = np.round(r["fvar"], 3)
-            g[reg + "_fmean_rt"][i] = np.round(fmean + lineT[-1], 3)
-            g[reg + "_raw_fmean"][i] = r["fmean"]
-            g[reg + "_raw_fvar"][i] = r["fvar"]
-            g[reg + "_raw_fmean_rt"][i] = r["fmean"] + lineT[-1]
+        if m.shape[0] == 0:
+            return out
+        ci_a, k_a, year_a = m[:, 0], m[:, 1], m[:, 2]
+        fmean_raw, fvar_raw = raw["fmean"].astype(np.float64), raw["fvar"].astype(np.float64)
+        fmean = np.round(fmean_raw, 3)
+        fvar = np.round(fvar_raw, 3)
+        for ci, cfg in enumerate(self.cfgs):
+            for k, reg in enumerate(cfg.regions):
+                sel = np.nonzero((ci_a == ci) & (k_a == k))[0]
+                if sel.size == 0:
+                    continue
+                g = out.setdefault(cfg.name, {})
+                years = year_a[sel]
+                row = years - (self.fmin - 1) - 1
+                tr = self.sie_trend[reg][row]                        # (slope, intercept) of that year's window
+                line_last = (years - FIRST_YEAR) * tr[:, 0] + tr[:, 1]   # lineT[-1], June1st_retro.py:285-286
+                i = years - self.fmin
+                for key, val in (("_fmean", fmean[sel]), ("_fvar", fvar[sel]),
+                                 ("_fmean_rt", np.round(fmean[sel] + line_last, 3)),
+                                 ("_raw_fmean", fmean_raw[sel]), ("_raw_fvar", fvar_raw[sel]),
+                                 ("_raw_fmean_rt", fmean_raw[sel] + line_last)):
+                    arr = g.setdefault(reg + key, np.full(len(self.years), np.nan))
+                    arr[i] = val
         return out
 
     def skill(self, gpr):
