@@ -90,6 +90,32 @@ def test_network_full_north_grid(lib_built):
     assert len(n.V) >= 2
 
 
+def test_network_south_grid(lib_built):
+    """81x81 (config 3, south/February1st.py:79): 6561 cells do not fit the all-on-chip layout of k_area_level, so
+    this exercises the placement that evicts integer arrays to global scratch."""
+    from oracle.gp import detrend as odetrend
+    data, _ = syn.make_field(81, 81, 20, 5)
+    odt, _ = odetrend(data)
+    kw = {"area": syn.make_psar(81, 81)}
+    n = _product(odt, False, kw)
+    o = _oracle(odt, False, kw)
+    compare_networks(n, o, odt)
+    assert len(n.V) >= 2
+
+
+def test_network_giant_area(lib_built):
+    """A coherent field whose largest area has ~2400 cells: areas beyond one pairwise leaf (re-summing growth path,
+    multi-level pairwise trees) and beyond the 1024-row dense block of the merge step (gather path)."""
+    from oracle.gp import detrend as odetrend
+    data, _ = syn.make_field(64, 64, 24, 5, n_modes=3, noise=0.08, blob=(14., 24.))
+    odt, _ = odetrend(data)
+    kw = {"area": syn.make_psar(64, 64)}
+    n = _product(odt, False, kw)
+    o = _oracle(odt, False, kw)
+    assert max(len(v) for v in o.V.values()) > 1024
+    compare_networks(n, o, odt)
+
+
 def test_errors_like_reference(lib_built):
     from seaiceextentforecasting_b200.ComplexNetworks import Network
     rng = np.random.default_rng(0)
