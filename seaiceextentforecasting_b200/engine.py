@@ -93,7 +93,8 @@ class NetworkBatch:
         self.first_nan = torch.empty((B_,), dtype=i32, device=dev)
         self.status = torch.zeros((B_,), dtype=i32, device=dev)
         self.R = torch.empty((B_, ldn, ldn), dtype=f64, device=dev) if keep_R else None
-        self.tau_scratch_bytes = int(self.lib.sie_corr_tau_scratch_bytes(B_, ldn))
+        self.tau_scratch_bytes = int(self.lib.sie_corr_tau_scratch_bytes(B_, ldn)) + \
+            B_ * int(self.lib.sie_corr_tau_scratch_bytes(1, ldn)) + 4096   # room for per-range slices
         self.tau_scratch = torch.empty((self.tau_scratch_bytes + 7) // 8, dtype=f64, device=dev)
         self.tau_sum = torch.empty((B_,), dtype=f64, device=dev)
         self.tau_cnt = torch.empty((B_,), dtype=torch.int64, device=dev)
@@ -115,59 +116,83 @@ class NetworkBatch:
         self.launches = 0
 
     # ---- stages -------------------------------------------------------------------------------
-    def detrend_zscore(self, fields, job_field, job_T, do_detrend=True):
+    # Every stage takes an optional job range `jr = (j0, j1)`: jobs are independent and every per-job array is
+    # job-major, so a sub-batch is the same C-ABI call on offset pointers.  The retrospective sweep uses this to run
+    # two waves (short / long windows) on separate streams.
+    def _range(self, jr):
+        j0, j1 = (0, self.B) if jr is None else (int(jr[0]), int(jr[1]))
+        assert 0 <= j0 < j1 <= self.B
+        return j0, j1
+
+    def detrend_zscore(self, fields, job_field, job_T, do_detrend=True, jr=None):
         """K1.  fields: device [F, C, Tstride]; job_field/job_T: device int32 [B]."""
+        j0, j1 = self._range(jr)
         self.job_T = job_T
         dt = self.dt if do_detrend else fields
         if not do_detrend:
             assert fields.shape[0] == self.B, "pass-through mode needs one field per job"
             self.dt = fields
-        rc = self.lib.sie_detrend_zscore(_ptr(fields), _ptr(job_field), _ptr(job_T), self.B, self.C, self.Tstride,
-                                         self.Tp, 1 if do_detrend else 0, _ptr(dt), _ptr(self.trend), _ptr(self.z),
-                                         _ptr(self.node_cell), _ptr(self.cell_node), _ptr(self.n_nodes),
-                                         _ptr(self.first_nan), _ptr(self.status), self.ldn, _stream())
+        rc = self.lib.sie_detrend_zscore(_ptr(fields), _ptr(job_field[j0:]), _ptr(job_T[j0:]), j1 - j0, self.C,
+                                         self.Tstride, self.Tp, 1 if do_detrend else 0, _ptr(dt[j0:]),
+                                         _ptr(self.trend[j0:]), _ptr(self.z[j0:]), _ptr(self.node_cell[j0:]),
+                                         _ptr(self.cell_node[j0:]), _ptr(self.n_nodes[j0:]), _ptr(self.first_nan[j0:]),
+                                         _ptr(self.status[j0:]), self.ldn, _stream())
         _lib.check(rc, "sie_detrend_zscore")
         self.launches += 3
 
-    def corr_tau(self, r_crit, store_R=True, shard_rank=0, shard_count=1):
+    def corr_tau(self, r_crit, store_R=True, shard_rank=0, shard_count=1, jr=None):
         """K2.  r_crit: device float64 [B]."""
-        R = self.R if store_R else None
-        rc = self.lib.sie_corr_tau(_ptr(self.z), _ptr(self.n_nodes), _ptr(self.job_T), _ptr(r_crit), self.B,
-                                   self.ldn, self.Tp, _ptr(R), _ptr(self.tau_scratch), self.tau_scratch_bytes,
-                                   _ptr(self.tau_sum), _ptr(self.tau_cnt), _ptr(self.tau), shard_rank, shard_count,
-                                   _stream())
+        j0, j1 = self._range(jr)
+        R = self.R[j0:] if store_R else None
+        # each job range owns a disjoint slice of the tile-partial scratch so ranges can run concurrently
+        per_job = int(self.lib.sie_corr_tau_scratch_bytes(1, self.ldn))
+        off = (j0 * per_job + 255) // 256 * 256 // 8
+        nbytes = int(self.lib.sie_corr_tau_scratch_bytes(j1 - j0, self.ldn))
+        scratch = self.tau_scratch[off:]
+        assert scratch.numel() * 8 >= nbytes
+        rc = self.lib.sie_corr_tau(_ptr(self.z[j0:]), _ptr(self.n_nodes[j0:]), _ptr(self.job_T[j0:]),
+                                   _ptr(r_crit[j0:]), j1 - j0, self.ldn, self.Tp, _ptr(R), _ptr(scratch),
+                                   scratch.numel() * 8, _ptr(self.tau_sum[j0:]), _ptr(self.tau_cnt[j0:]),
+                                   _ptr(self.tau[j0:]), shard_rank, shard_count, _stream())
         _lib.check(rc, "sie_corr_tau")
         self.launches += 3
 
-    def area_level(self):
+    def area_level(self, jr=None):
         """K3 + K4/K5."""
-        rc = self.lib.sie_corr_stencil(_ptr(self.R), _ptr(self.node_cell), _ptr(self.cell_node), _ptr(self.n_nodes),
-                                       self.B, self.X, self.Y, self.ldn, int(self.latlon), _ptr(self.stencil),
-                                       _stream())
+        j0, j1 = self._range(jr)
+        n = j1 - j0
+        rc = self.lib.sie_corr_stencil(_ptr(self.R[j0:]), _ptr(self.node_cell[j0:]), _ptr(self.cell_node[j0:]),
+                                       _ptr(self.n_nodes[j0:]), n, self.X, self.Y, self.ldn, int(self.latlon),
+                                       _ptr(self.stencil[j0:]), _stream())
         _lib.check(rc, "sie_corr_stencil")
-        rc = self.lib.sie_area_level(_ptr(self.R), _ptr(self.stencil), _ptr(self.node_cell), _ptr(self.cell_node),
-                                     _ptr(self.n_nodes), _ptr(self.tau), _ptr(self.first_nan), self.B, self.X,
-                                     self.Y, self.ldn, int(self.latlon), self.MA, _ptr(self.area_cells),
-                                     _ptr(self.area_start), _ptr(self.area_key), _ptr(self.n_areas),
-                                     _ptr(self.label), _ptr(self.status), _ptr(self.area_scratch),
-                                     self.area_scratch_bytes, _ptr(self.area_work), _stream())
+        per_job = self.area_scratch_bytes // self.B          # sie_area_level_scratch_bytes is linear in B
+        scratch = self.area_scratch[j0 * per_job // 8:]
+        rc = self.lib.sie_area_level(_ptr(self.R[j0:]), _ptr(self.stencil[j0:]), _ptr(self.node_cell[j0:]),
+                                     _ptr(self.cell_node[j0:]), _ptr(self.n_nodes[j0:]), _ptr(self.tau[j0:]),
+                                     _ptr(self.first_nan[j0:]), n, self.X, self.Y, self.ldn, int(self.latlon),
+                                     self.MA, _ptr(self.area_cells[j0:]), _ptr(self.area_start[j0:]),
+                                     _ptr(self.area_key[j0:]), _ptr(self.n_areas[j0:]), _ptr(self.label[j0:]),
+                                     _ptr(self.status[j0:]), _ptr(scratch), n * per_job,
+                                     _ptr(self.area_work[j0:]), _stream())
         _lib.check(rc, "sie_area_level")
         self.launches += 2
 
-    def intra_links(self, scale):
+    def intra_links(self, scale, jr=None):
         """K6.  scale: device float64 [C] (already square-rooted weights)."""
-        rc = self.lib.sie_intra_links(_ptr(self.dt), _ptr(scale), _ptr(self.job_T), _ptr(self.area_cells),
-                                      _ptr(self.area_start), _ptr(self.n_areas), _ptr(self.label), self.B, self.C,
-                                      self.Tstride, self.MA, _ptr(self.anomaly), _ptr(self.links),
-                                      _ptr(self.strength), _ptr(self.strengthmap), _stream())
+        j0, j1 = self._range(jr)
+        rc = self.lib.sie_intra_links(_ptr(self.dt[j0:]), _ptr(scale), _ptr(self.job_T[j0:]),
+                                      _ptr(self.area_cells[j0:]), _ptr(self.area_start[j0:]),
+                                      _ptr(self.n_areas[j0:]), _ptr(self.label[j0:]), j1 - j0, self.C, self.Tstride,
+                                      self.MA, _ptr(self.anomaly[j0:]), _ptr(self.links[j0:]),
+                                      _ptr(self.strength[j0:]), _ptr(self.strengthmap[j0:]), _stream())
         _lib.check(rc, "sie_intra_links")
         self.launches += 3
 
-    def build(self, fields, job_field, job_T, r_crit, scale, do_detrend=True):
-        self.detrend_zscore(fields, job_field, job_T, do_detrend)
-        self.corr_tau(r_crit)
-        self.area_level()
-        self.intra_links(scale)
+    def build(self, fields, job_field, job_T, r_crit, scale, do_detrend=True, jr=None):
+        self.detrend_zscore(fields, job_field, job_T, do_detrend, jr)
+        self.corr_tau(r_crit, jr=jr)
+        self.area_level(jr)
+        self.intra_links(scale, jr)
 
     # ---- host views ---------------------------------------------------------------------------
     def areas_to_host(self):

@@ -103,13 +103,20 @@ class GpBatch:
         self.scratch = torch.empty((self.scratch_bytes + 7) // 8, dtype=torch.float64, device="cuda")
         self.out = torch.empty(self.P * GP_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
 
-    def run(self, prob_dev, y_dev, sic: NetworkBatch, sst: NetworkBatch | None):
+    def run(self, prob_dev, y_dev, sic: NetworkBatch, sst: NetworkBatch | None, pr=None, out=None):
+        """`pr = (p0, p1)`: run only that range of problems (records p0..p1-1 of prob_dev / out); each range needs its
+        own GpBatch when ranges run concurrently (the scratch holds the work queue); `out`: result buffer of the
+        whole problem list (default: this batch's own)."""
+        p0, p1 = (0, self.P) if pr is None else (int(pr[0]), int(pr[1]))
+        out = self.out if out is None else out
+        isz = GP_PROBLEM_DTYPE.itemsize
+        osz = GP_RESULT_DTYPE.itemsize
         rc = self.lib.sie_gp_forecast(
-            _ptr(prob_dev), self.P, _ptr(y_dev), _ptr(sic.anomaly), _ptr(sic.n_areas), sic.MA, sic.Tstride,
+            _ptr(prob_dev[p0 * isz:]), p1 - p0, _ptr(y_dev), _ptr(sic.anomaly), _ptr(sic.n_areas), sic.MA, sic.Tstride,
             _ptr(sst.anomaly) if sst is not None else C.c_void_p(0),
             _ptr(sst.n_areas) if sst is not None else C.c_void_p(0),
             sst.MA if sst is not None else 0, sst.Tstride if sst is not None else 0,
-            self.max_pred, _ptr(self.out), _ptr(self.scratch), self.scratch_bytes, _stream())
+            self.max_pred, _ptr(out[p0 * osz:]), _ptr(self.scratch), self.scratch_bytes, _stream())
         _lib.check(rc, "sie_gp_forecast")
 
     def results(self):
@@ -298,7 +305,7 @@ class RetrospectiveSweep:
     """
 
     def __init__(self, config_names, sic_fields, sie, fmin, fmax, psar, sst_field=None, sst_lat=None,
-                 significance=0.01, max_areas=None, max_pred=384, rank=0, world=1):
+                 significance=0.01, max_areas=None, max_pred=384, rank=0, world=1, wave_T=12):
         require_cuda()
         self.plan = plan = SweepPlan(config_names, sie, fmin, fmax, significance, rank, world)
         self.cfgs, self.years, self.fmin, self.fmax = plan.cfgs, plan.years, plan.fmin, plan.fmax
@@ -325,6 +332,25 @@ class RetrospectiveSweep:
         self.n_forecasts = plan.P
         self.gp = GpBatch(max(1, self.P), max_pred=max_pred)
         self._side = None
+        # Two waves: (B) long windows, whose domain growth is the slow stage and whose GP problems are small, and
+        # (A) short windows (T <= wave_T), whose networks finish early and whose GP problems (many small areas ->
+        # up to ~160 predictors) are the expensive ones.  Jobs and problems are ordered by descending year, so each
+        # wave is a contiguous range; wave A's GP then overlaps wave B's domain growth.
+        self.wave_T = int(wave_T)
+        T = plan.job_T
+        self.jB = int((T > self.wave_T).sum())                       # SIC jobs [0, jB) = wave B, [jB, nJ) = wave A
+        assert (T[:self.jB] > self.wave_T).all() and (T[self.jB:] <= self.wave_T).all()
+        self.sB = int((plan.sst_T > self.wave_T).sum()) if self.use_sst else 0
+        prob_T = plan.job_T[plan.prob["job_sic"]] if plan.P else np.zeros(0, dtype=np.int32)
+        self.pB = int((prob_T > self.wave_T).sum())                  # problems [0, pB) only read wave-B... see below
+        ok = plan.P > 0 and (prob_T[:self.pB] > self.wave_T).all() and (prob_T[self.pB:] <= self.wave_T).all()
+        if self.use_sst and plan.P:
+            ps = plan.prob["job_sst"][self.pB:]
+            ok = ok and bool((ps[ps >= 0] >= self.sB).all())         # wave-A problems only read wave-A SST networks
+        self.two_waves = bool(ok and 0 < self.jB < len(plan.jobs) and 0 < self.pB < plan.P and
+                              (not self.use_sst or 0 < self.sB < len(plan.sst_years)))
+        self.gpA = GpBatch(max(1, self.P - self.pB), max_pred=max_pred) if self.two_waves else None
+        self._streams = None
         # pinned staging buffers so every step pays a real host->device copy
         self._pin = {name: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
                      for name, arr in self._host_inputs().items()}
@@ -349,10 +375,12 @@ class RetrospectiveSweep:
         self.dev = {k: t.to("cuda", non_blocking=True) for k, t in self._pin.items()}
         return self.dev
 
-    def compute(self, marks=None):
+    def compute(self, marks=None, waves=None):
         """Enqueue the whole hot path on the current stream (no host sync).  `marks`: optional list that receives
-        (stage name, torch.cuda.Event) pairs recorded after each stage, for per-kernel timing."""
+        (stage name, torch.cuda.Event) pairs recorded after each stage, for per-kernel timing.  `waves`: 1 = one
+        batch per grid (stage timing), 2 = short/long-window waves on separate streams (default when possible)."""
         d = self.dev
+        two = self.two_waves if waves is None else (waves == 2 and self.two_waves)
 
         def mark(name):
             if marks is not None:
@@ -360,36 +388,69 @@ class RetrospectiveSweep:
                 ev.record()
                 marks.append((name, ev))
 
-        def chain(tag, eng, fields, job_field, job_T, rcrit, scale):
+        def chain(tag, eng, fields, job_field, job_T, rcrit, scale, jr=None):
             mark(tag + ".start")
-            eng.detrend_zscore(fields, job_field, job_T, do_detrend=True)
+            eng.detrend_zscore(fields, job_field, job_T, do_detrend=True, jr=jr)
             mark(tag + ".detrend_zscore")
-            eng.corr_tau(rcrit)
+            eng.corr_tau(rcrit, jr=jr)
             mark(tag + ".corr_tau")
-            eng.area_level()
+            eng.area_level(jr=jr)
             mark(tag + ".area_level")
-            eng.intra_links(scale)
+            eng.intra_links(scale, jr=jr)
             mark(tag + ".intra_links")
 
         main = torch.cuda.current_stream()
+        if not two:
+            if self.sst is not None:
+                # the SST networks are independent of the SIC ones: run their chain on a side stream so the two
+                # latency-bound domain-growth kernels share the SMs instead of running back to back
+                if self._side is None:
+                    self._side = torch.cuda.Stream()
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    chain("sst", self.sst, d["sst"], d["sst_field_idx"], d["sst_T"], d["sst_rcrit"], d["lat"])
+            chain("sic", self.sic, d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"])
+            if self.sst is not None:
+                main.wait_stream(self._side)
+            mark("gp.start")
+            self.gp.run(d["prob"], d["y"], self.sic, self.sst)
+            mark("gp")
+            return
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(priority=-1) for _ in range(3)]
+        sA, sSb, sSa = self._streams
+        nJ, nS = self.sic.B, (self.sst.B if self.sst is not None else 0)
+        for st in self._streams:
+            st.wait_stream(main)
+        with torch.cuda.stream(sA):            # wave A: short windows -> the big GP problems
+            chain("sicA", self.sic, d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"], (self.jB, nJ))
         if self.sst is not None:
-            # the SST networks are independent of the SIC ones: run their chain on a side stream so the two
-            # latency-bound domain-growth kernels share the SMs instead of running back to back
-            if self._side is None:
-                self._side = torch.cuda.Stream()
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                chain("sst", self.sst, d["sst"], d["sst_field_idx"], d["sst_T"], d["sst_rcrit"], d["lat"])
-        chain("sic", self.sic, d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"])
+            with torch.cuda.stream(sSa):
+                chain("sstA", self.sst, d["sst"], d["sst_field_idx"], d["sst_T"], d["sst_rcrit"], d["lat"], (self.sB, nS))
+            with torch.cuda.stream(sSb):
+                chain("sstB", self.sst, d["sst"], d["sst_field_idx"], d["sst_T"], d["sst_rcrit"], d["lat"], (0, self.sB))
+        chain("sicB", self.sic, d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"], (0, self.jB))
+        with torch.cuda.stream(sA):
+            chainA_done = torch.cuda.Event()
+            chainA_done.record()
+            if self.sst is not None:
+                sA.wait_stream(sSa)
+            mark("gpA.start")
+            self.gpA.run(d["prob"], d["y"], self.sic, self.sst, (self.pB, self.P), out=self.gp.out)
+            mark("gpA")
         if self.sst is not None:
-            main.wait_stream(self._side)
-        mark("gp.start")
-        self.gp.run(d["prob"], d["y"], self.sic, self.sst)
-        mark("gp")
+            main.wait_stream(sSb)
+            main.wait_stream(sSa)
+        main.wait_event(chainA_done)            # wave-B problems with a previous-year network may read wave-A jobs
+        mark("gpB.start")
+        self.gp.run(d["prob"], d["y"], self.sic, self.sst, (0, self.pB))
+        mark("gpB")
+        main.wait_stream(sA)                    # the step is complete on `main` once wave A's GP has finished too
 
     def kernel_launches(self):
-        """Kernels of libsie_b200 enqueued by one compute(): 11 per network batch + 2 GP kernels."""
-        return 11 * (2 if self.use_sst else 1) + 2
+        """Kernels of libsie_b200 enqueued by one compute(): 11 per network batch (per wave) + 2 per GP batch."""
+        w = 2 if self.two_waves else 1
+        return w * (11 * (2 if self.use_sst else 1) + 2)
 
     def download(self):
         """Device -> host read of the GP results (synchronises)."""
