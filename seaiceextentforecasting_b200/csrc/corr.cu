@@ -15,9 +15,12 @@
 
 namespace {
 
-constexpr int TILE = 128;
-constexpr int NWARP = 16;       // 4 x 4 warps, each a 32 x 32 sub-tile = 4 x 4 DMMA blocks
+constexpr int TILE = 128;        // rows of a tile (and the granularity of ldn / row shards)
+constexpr int TILE_N = 64;       // columns of a tile
+constexpr int NWARP = 8;         // 4 x 2 warps, each a 32 x 32 sub-tile = 4 x 4 DMMA blocks
 constexpr int NTHREADS = NWARP * 32;
+constexpr int CS_LD = TILE_N + 1;  // row stride of the staged output tile (odd: conflict-free column reads)
+constexpr int CTAS_PER_SM = 2;   // co-resident CTAs in different phases: one's stores overlap another's MMAs
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -59,10 +62,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// per-job tile bookkeeping for this shard: rows bi = rank, rank+count, ... each with (nb - bi) tiles
-__device__ __host__ __forceinline__ long long shard_tiles_before(int q, int nb, int rank, int count) {
-  // tiles in my first q rows
-  return (long long)q * (nb - rank) - (long long)count * q * (q - 1) / 2;
+// per-job tile bookkeeping for this shard: tile rows bi = rank, rank+count, ... ; row bi owns the column blocks
+// (64 wide) 2*bi .. nc-1, i.e. everything on or right of the diagonal block
+__device__ __host__ __forceinline__ long long shard_tiles_before(int q, int nc, int rank, int count) {
+  // tiles in my first q rows: sum_{q'<q} (nc - 2*(rank + q'*count))
+  return (long long)q * (nc - 2 * rank) - (long long)count * q * (q - 1);
 }
 __device__ __host__ __forceinline__ int shard_rows(int nb, int rank, int count) {
   return nb > rank ? (nb - rank + count - 1) / count : 0;
@@ -76,94 +80,79 @@ __global__ void k_tile_prefix(const int32_t* __restrict__ n_nodes, int B, int ld
       prefix[b] = acc;
       int N = min(n_nodes[b], ldn);
       int nb = (N + TILE - 1) / TILE;
+      int nc = 2 * nb;                       // column blocks, padded to whole row blocks (z rows beyond N are zero)
       int rows = shard_rows(nb, rank, count);
-      acc += shard_tiles_before(rows, nb, rank, count);
+      acc += shard_tiles_before(rows, nc, rank, count);
     }
     prefix[B] = acc;
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+// item -> (job, 128-row block, 64-column block), written once so the tile loop decodes with one 16-byte load
+__global__ void k_tile_table(const int32_t* __restrict__ n_nodes, int ldn, int rank, int count,
+                             const long long* __restrict__ prefix, int4* __restrict__ table) {
+  const int b = blockIdx.x, q = blockIdx.y;
+  const int N = min(n_nodes[b], ldn);
+  const int nb = (N + TILE - 1) / TILE, nc = 2 * nb;
+  if (q >= shard_rows(nb, rank, count)) return;
+  const int bi = rank + q * count;
+  const long long base = prefix[b] + shard_tiles_before(q, nc, rank, count);
+  for (int t = threadIdx.x; t < nc - 2 * bi; t += blockDim.x) table[base + t] = make_int4(b, bi, 2 * bi + t, 0);
+}
+
+__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM)
 k_corr_tiles(const double* __restrict__ z, const int32_t* __restrict__ n_nodes,
              const int32_t* __restrict__ job_T, const double* __restrict__ r_crit,
-             const long long* __restrict__ prefix, int B, int ldn, int Tp, double* __restrict__ R,
-             double* __restrict__ tile_part, int rank, int count) {
+             const long long* __restrict__ prefix, const int4* __restrict__ table, int B, int ldn, int Tp,
+             double* __restrict__ R, double* __restrict__ tile_part) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int panel = TILE * Tp;                       // doubles per panel
-  double* stage_base = reinterpret_cast<double*>(smem_raw);
-  // [stage][A|B][128][Tp]
-  __shared__ uint64_t full_bar[2], empty_bar[2];
+  double* sA = reinterpret_cast<double*>(smem_raw);          // [128][Tp]
+  double* sB = sA + (size_t)TILE * Tp;                       // [64][Tp]
+  __shared__ uint64_t full_bar, empty_bar;
   __shared__ double red_sum[NWARP];
   __shared__ double red_cnt[NWARP];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wr = warp >> 2, wc = warp & 3;           // warp position in the 4x4 grid
+  const int wr = warp >> 1, wc = warp & 1;           // warp position in the 4x2 grid
   if (tid == 0) {
-    mbar_init(&full_bar[0], 1);
-    mbar_init(&full_bar[1], 1);
-    mbar_init(&empty_bar[0], NWARP);
-    mbar_init(&empty_bar[1], NWARP);
+    mbar_init(&full_bar, 1);
+    mbar_init(&empty_bar, NWARP);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   const long long total = prefix[B];
-  const uint32_t panel_bytes = (uint32_t)(panel * sizeof(double));
+  const uint32_t a_bytes = (uint32_t)((size_t)TILE * Tp * sizeof(double));
+  const uint32_t b_bytes = (uint32_t)((size_t)TILE_N * Tp * sizeof(double));
 
   auto decode = [&](long long item, int& b, int& bi, int& bj) {
-    int lo = 0, hi = B - 1;                          // last b with prefix[b] <= item
-    while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (prefix[mid] <= item) lo = mid; else hi = mid - 1;
-    }
-    b = lo;
-    long long t = item - prefix[b];
-    const int N = min(n_nodes[b], ldn);
-    const int nb = (N + TILE - 1) / TILE;
-    // my row index q: largest q with shard_tiles_before(q) <= t
-    double a = 0.5 * count, bb = (double)(nb - rank) + 0.5 * count;
-    double disc = bb * bb - 4.0 * a * (double)t;
-    int q = (int)((bb - sqrt(disc > 0 ? disc : 0.0)) / (2.0 * a));
-    if (q < 0) q = 0;
-    while (q > 0 && shard_tiles_before(q, nb, rank, count) > t) --q;
-    while (shard_tiles_before(q + 1, nb, rank, count) <= t) ++q;
-    bi = rank + q * count;
-    bj = bi + (int)(t - shard_tiles_before(q, nb, rank, count));
+    const int4 e = table[item];
+    b = e.x; bi = e.y; bj = e.z;
   };
 
-  auto issue = [&](long long item, int stage) {
+  auto issue = [&](long long item) {
     int b, bi, bj;
     decode(item, b, bi, bj);
-    double* sA = stage_base + (size_t)stage * 2 * panel;
-    double* sB = sA + panel;
     const double* gA = z + ((size_t)b * ldn + (size_t)bi * TILE) * Tp;
-    const double* gB = z + ((size_t)b * ldn + (size_t)bj * TILE) * Tp;
-    mbar_expect_tx(&full_bar[stage], 2 * panel_bytes);
-    bulk_g2s(sA, gA, panel_bytes, &full_bar[stage]);
-    bulk_g2s(sB, gB, panel_bytes, &full_bar[stage]);
+    const double* gB = z + ((size_t)b * ldn + (size_t)bj * TILE_N) * Tp;
+    mbar_expect_tx(&full_bar, a_bytes + b_bytes);
+    bulk_g2s(sA, gA, a_bytes, &full_bar);
+    bulk_g2s(sB, gB, b_bytes, &full_bar);
   };
 
   long long item = blockIdx.x;
   if (item >= total) return;
-  if (tid == 0) issue(item, 0);
+  if (tid == 0) issue(item);
 
+  int eph = 0;                                       // uses of empty_bar so far (its phase)
   for (int it = 0; item < total; ++it, item += gridDim.x) {
-    const int stage = it & 1;
-    const long long next = item + gridDim.x;
-    if (tid == 0 && next < total) {
-      const int ns = stage ^ 1;
-      if (it >= 1) mbar_wait(&empty_bar[ns], ((it - 1) >> 1) & 1);   // previous user of that stage is done
-      issue(next, ns);
-    }
     int b, bi, bj;
     decode(item, b, bi, bj);
     const int N = min(n_nodes[b], ldn);
     const int ksteps = (job_T[b] + 3) >> 2;
     const double rc = r_crit[b];
 
-    mbar_wait(&full_bar[stage], (it >> 1) & 1);
-    const double* sA = stage_base + (size_t)stage * 2 * panel;
-    const double* sB = sA + panel;
+    mbar_wait(&full_bar, it & 1);
 
     double acc[4][4][2];
 #pragma unroll
@@ -185,19 +174,79 @@ k_corr_tiles(const double* __restrict__ z, const int32_t* __restrict__ n_nodes,
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
+    const int row0 = bi * TILE, col0 = bj * TILE_N;
+    const bool diag_tile = (col0 < row0 + TILE);     // the tile touches the diagonal band of its row block
+    const bool staged = (R != nullptr) && !diag_tile;   // off-diagonal tiles are written through shared memory
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[stage]);   // smem stage free: the next load overlaps the epilogue
-
+    if (!staged) {
+      if (lane == 0) mbar_arrive(&empty_bar);        // this warp no longer reads the panels
+      if (tid == 0 && item + gridDim.x < total) {    // refill them as soon as every warp is done: the load of the
+        mbar_wait(&empty_bar, eph & 1);              // next tile overlaps this tile's epilogue
+        issue(item + gridDim.x);
+      }
+      ++eph;
+    }
     // ---- epilogue: clip, NaN diagonal, mirrored store, tau partials
     double lsum = 0.0, lcnt = 0.0;
     double* Rb = R ? R + (size_t)b * ldn * ldn : nullptr;
-    const bool diag_tile = (bi == bj);
+    if (staged) {
+      // Every element of an off-diagonal tile is above the diagonal: it is written twice, as R[gi][gj] and R[gj][gi].
+      // Stage the clipped tile in shared memory (over the operand panels, once every warp has finished its MMAs) and
+      // write whole rows: 512-byte runs for the tile itself, 1-KB runs for its transpose, instead of 64-byte pieces
+      // scattered over 192 DRAM pages.
+      __syncthreads();                               // all warps done with the panels
+      double* Cs = reinterpret_cast<double*>(smem_raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int li = wr * 32 + i * 8 + (lane >> 2);
+        const int gi = row0 + li;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int lj = wc * 32 + j * 8 + 2 * (lane & 3);
+          const int gj = col0 + lj;
+          double v0 = acc[i][j][0], v1 = acc[i][j][1];
+          v0 = v0 > 1.0 ? 1.0 : (v0 < -1.0 ? -1.0 : v0);   // np.clip keeps NaN
+          v1 = v1 > 1.0 ? 1.0 : (v1 < -1.0 ? -1.0 : v1);
+          Cs[li * CS_LD + lj] = v0;
+          Cs[li * CS_LD + lj + 1] = v1;
+          if (gi < N) {
+            if (gj < N && v0 >= 0.0 && v0 > rc) { lsum += v0; lcnt += 1.0; }
+            if (gj + 1 < N && v1 >= 0.0 && v1 > rc) { lsum += v1; lcnt += 1.0; }
+          }
+        }
+      }
+      __syncthreads();
+      // the tile: row r -> 64 doubles, lane l writes columns 2l, 2l+1
+      for (int r = warp; r < TILE; r += NWARP) {
+        const int gi = row0 + r, gj = col0 + 2 * lane;
+        if (gi >= N) break;
+        const double v0 = Cs[r * CS_LD + 2 * lane], v1 = Cs[r * CS_LD + 2 * lane + 1];
+        double* dst = Rb + (size_t)gi * ldn + gj;
+        if (gj + 1 < N) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+        else if (gj < N) dst[0] = v0;
+      }
+      // its transpose: column c -> row col0+c of R, 128 doubles, lane l writes columns 2l, 2l+1 and 64+2l, 64+2l+1
+      for (int c = warp; c < TILE_N; c += NWARP) {
+        const int gj = col0 + c;
+        if (gj >= N) break;
+        double* dst = Rb + (size_t)gj * ldn + row0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = 64 * h + 2 * lane;
+          const double v0 = Cs[r * CS_LD + c], v1 = Cs[(r + 1) * CS_LD + c];
+          if (row0 + r + 1 < N) *reinterpret_cast<double2*>(dst + r) = make_double2(v0, v1);
+          else if (row0 + r < N) dst[r] = v0;
+        }
+      }
+      __syncthreads();                               // staging buffer free: the next panels may land
+      if (tid == 0 && item + gridDim.x < total) issue(item + gridDim.x);
+    } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int gi = bi * TILE + wr * 32 + i * 8 + (lane >> 2);
+      const int gi = row0 + wr * 32 + i * 8 + (lane >> 2);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int gj = bj * TILE + wc * 32 + j * 8 + 2 * (lane & 3);
+        const int gj = col0 + wc * 32 + j * 8 + 2 * (lane & 3);
         double v0 = acc[i][j][0], v1 = acc[i][j][1];
         v0 = v0 > 1.0 ? 1.0 : (v0 < -1.0 ? -1.0 : v0);   // np.clip keeps NaN
         v1 = v1 > 1.0 ? 1.0 : (v1 < -1.0 ? -1.0 : v1);
@@ -225,6 +274,7 @@ k_corr_tiles(const double* __restrict__ z, const int32_t* __restrict__ n_nodes,
           }
         }
       }
+    }
     }
     // deterministic CTA reduction of the tile partial (fixed shuffle tree, fixed warp order)
 #pragma unroll
@@ -296,8 +346,8 @@ __global__ void k_stencil(const double* __restrict__ R, const int32_t* __restric
 
 extern "C" size_t sie_corr_tau_scratch_bytes(int B, int ldn) {
   long long nb = (ldn + TILE - 1) / TILE;
-  long long tiles = (long long)B * nb * (nb + 1) / 2;
-  return (size_t)(tiles * 2 * sizeof(double) + (size_t)(B + 1) * sizeof(long long) + 256);
+  long long tiles = (long long)B * nb * (nb + 1);      // 128 x 64 tiles on or right of the diagonal blocks
+  return (size_t)(tiles * (2 * sizeof(double) + sizeof(int4)) + (size_t)(B + 1) * sizeof(long long) + 512);
 }
 
 extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32_t* job_T,
@@ -310,7 +360,9 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
   SIE_CHECK_ARG(shard_count >= 1 && shard_rank >= 0 && shard_rank < shard_count, "bad shard");
   SIE_CHECK_ARG(tile_part_bytes >= sie_corr_tau_scratch_bytes(B, ldn), "tile_part scratch too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)2 * 2 * TILE * Tp * sizeof(double);
+  const size_t smem_panels = (size_t)(TILE + TILE_N) * Tp * sizeof(double);
+  const size_t smem_stage = R ? (size_t)TILE * CS_LD * sizeof(double) : 0;   // output tile staged over the panels
+  const size_t smem = smem_panels > smem_stage ? smem_panels : smem_stage;
   int dev = 0, sms = 0, max_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -319,18 +371,23 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
     sie_set_error("sie_corr_tau: Tp=%d needs %zu B of shared memory (> %d)", Tp, smem, max_optin);
     return SIE_ERR_UNSUPPORTED;
   }
-  // scratch layout: [prefix (B+1) int64][pad to 256][tile partials]
+  // scratch layout: [prefix (B+1) int64][pad to 256][tile partials][pad to 256][item table]
   long long* prefix = reinterpret_cast<long long*>(tile_part);
   size_t off = (((size_t)(B + 1) * sizeof(long long)) + 255) / 256 * 256;
   double* parts = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tile_part) + off);
+  long long nb = ldn / TILE;
+  long long max_items = (long long)B * nb * (nb + 1);
+  size_t off2 = (off + (size_t)max_items * 2 * sizeof(double) + 255) / 256 * 256;
+  int4* table = reinterpret_cast<int4*>(reinterpret_cast<unsigned char*>(tile_part) + off2);
+  SIE_CHECK_ARG(off2 + (size_t)max_items * sizeof(int4) <= tile_part_bytes, "tile_part scratch too small");
   k_tile_prefix<<<1, 32, 0, st>>>(n_nodes, B, ldn, shard_rank, shard_count, prefix);
   SIE_CHECK_LAUNCH();
+  k_tile_table<<<dim3((unsigned)B, (unsigned)nb), 128, 0, st>>>(n_nodes, ldn, shard_rank, shard_count, prefix, table);
+  SIE_CHECK_LAUNCH();
   cudaFuncSetAttribute(k_corr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  long long nb = ldn / TILE;
-  long long max_items = (long long)B * nb * (nb + 1) / 2;
-  int grid = (int)(max_items < sms ? max_items : sms);
-  k_corr_tiles<<<grid, NTHREADS, smem, st>>>(z, n_nodes, job_T, r_crit, prefix, B, ldn, Tp, R, parts,
-                                             shard_rank, shard_count);
+  const long long slots = (long long)CTAS_PER_SM * sms;
+  int grid = (int)(max_items < slots ? max_items : slots);
+  k_corr_tiles<<<grid, NTHREADS, smem, st>>>(z, n_nodes, job_T, r_crit, prefix, table, B, ldn, Tp, R, parts);
   SIE_CHECK_LAUNCH();
   k_tau_finalize<<<(B + 3) / 4, 128, 0, st>>>(parts, prefix, B, tau_sum, tau_cnt, tau);
   SIE_CHECK_LAUNCH();

@@ -448,9 +448,10 @@ class RetrospectiveSweep:
         main.wait_stream(sA)                    # the step is complete on `main` once wave A's GP has finished too
 
     def kernel_launches(self):
-        """Kernels of libsie_b200 enqueued by one compute(): 11 per network batch (per wave) + 2 per GP batch."""
+        """Kernels of libsie_b200 enqueued by one compute(): 12 per network batch (K1: 3, K2: 4, K3-K5: 2, K6: 3), per
+        wave, + 2 per GP batch."""
         w = 2 if self.two_waves else 1
-        return w * (11 * (2 if self.use_sst else 1) + 2)
+        return w * (12 * (2 if self.use_sst else 1) + 2)
 
     def download(self):
         """Device -> host read of the GP results (synchronises)."""
