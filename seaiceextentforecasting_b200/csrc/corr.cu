@@ -150,7 +150,9 @@ k_corr_tiles(const double* __restrict__ z, const int32_t* __restrict__ n_nodes,
     decode(item, b, bi, bj);
     const int N = min(n_nodes[b], ldn);
     const int ksteps = (job_T[b] + 3) >> 2;
-    const double rc = r_crit[b];
+    const double rc_raw = r_crit[b];
+    // `R >= 0 && R > rc` (ComplexNetworks.py:44-45) as ONE compare: rc >= 0 -> R > rc; rc < 0 -> R > -denorm_min (R >= 0)
+    const double rc = (rc_raw < 0.0) ? -4.9406564584124654e-324 : rc_raw;
 
     mbar_wait(&full_bar, it & 1);
 
@@ -205,41 +207,70 @@ k_corr_tiles(const double* __restrict__ z, const int32_t* __restrict__ n_nodes,
           const int lj = wc * 32 + j * 8 + 2 * (lane & 3);
           const int gj = col0 + lj;
           double v0 = acc[i][j][0], v1 = acc[i][j][1];
-          v0 = v0 > 1.0 ? 1.0 : (v0 < -1.0 ? -1.0 : v0);   // np.clip keeps NaN
-          v1 = v1 > 1.0 ? 1.0 : (v1 < -1.0 ? -1.0 : v1);
+          if (!(fabs(v0) <= 1.0)) v0 = v0 > 1.0 ? 1.0 : (v0 < -1.0 ? -1.0 : v0);   // np.clip keeps NaN
+          if (!(fabs(v1) <= 1.0)) v1 = v1 > 1.0 ? 1.0 : (v1 < -1.0 ? -1.0 : v1);
           Cs[li * CS_LD + lj] = v0;
           Cs[li * CS_LD + lj + 1] = v1;
           if (gi < N) {
-            if (gj < N && v0 >= 0.0 && v0 > rc) { lsum += v0; lcnt += 1.0; }
-            if (gj + 1 < N && v1 >= 0.0 && v1 > rc) { lsum += v1; lcnt += 1.0; }
+            if (gj < N && v0 > rc) { lsum += v0; lcnt += 1.0; }
+            if (gj + 1 < N && v1 > rc) { lsum += v1; lcnt += 1.0; }
           }
         }
       }
       __syncthreads();
-      // the tile: row r -> 64 doubles, lane l writes columns 2l, 2l+1
-      for (int r = warp; r < TILE; r += NWARP) {
-        const int gi = row0 + r, gj = col0 + 2 * lane;
-        if (gi >= N) break;
-        const double v0 = Cs[r * CS_LD + 2 * lane], v1 = Cs[r * CS_LD + 2 * lane + 1];
-        double* dst = Rb + (size_t)gi * ldn + gj;
-        if (gj + 1 < N) *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
-        else if (gj < N) dst[0] = v0;
+      // the tile: row r -> 64 doubles, lane l writes columns 2l, 2l+1 (4 rows per trip: the shared-memory reads of
+      // all four are in flight before the first store)
+      {
+        const int gj = col0 + 2 * lane;
+        for (int r0 = warp; r0 < TILE; r0 += 4 * NWARP) {
+          double v[4][2];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * NWARP;
+            v[u][0] = Cs[r * CS_LD + 2 * lane];
+            v[u][1] = Cs[r * CS_LD + 2 * lane + 1];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int gi = row0 + r0 + u * NWARP;
+            if (gi < N) {
+              double* dst = Rb + (size_t)gi * ldn + gj;
+              if (gj + 1 < N) *reinterpret_cast<double2*>(dst) = make_double2(v[u][0], v[u][1]);
+              else if (gj < N) dst[0] = v[u][0];
+            }
+          }
+        }
       }
       // its transpose: column c -> row col0+c of R, 128 doubles, lane l writes columns 2l, 2l+1 and 64+2l, 64+2l+1
-      for (int c = warp; c < TILE_N; c += NWARP) {
-        const int gj = col0 + c;
-        if (gj >= N) break;
-        double* dst = Rb + (size_t)gj * ldn + row0;
+      for (int c0 = warp; c0 < TILE_N; c0 += 2 * NWARP) {
+        double v[2][2][2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int r = 64 * h + 2 * lane;
-          const double v0 = Cs[r * CS_LD + c], v1 = Cs[(r + 1) * CS_LD + c];
-          if (row0 + r + 1 < N) *reinterpret_cast<double2*>(dst + r) = make_double2(v0, v1);
-          else if (row0 + r < N) dst[r] = v0;
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r = 64 * h + 2 * lane, c = c0 + u * NWARP;
+            v[u][h][0] = Cs[r * CS_LD + c];
+            v[u][h][1] = Cs[(r + 1) * CS_LD + c];
+          }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int gj = col0 + c0 + u * NWARP;
+          if (gj < N) {
+            double* dst = Rb + (size_t)gj * ldn + row0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = 64 * h + 2 * lane;
+              if (row0 + r + 1 < N) *reinterpret_cast<double2*>(dst + r) = make_double2(v[u][h][0], v[u][h][1]);
+              else if (row0 + r < N) dst[r] = v[u][h][0];
+            }
+          }
         }
       }
       __syncthreads();                               // staging buffer free: the next panels may land
-      if (tid == 0 && item + gridDim.x < total) issue(item + gridDim.x);
+      if (tid == 0 && item + gridDim.x < total) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of Cs before the bulk copy lands
+        issue(item + gridDim.x);
+      }
     } else {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -254,8 +285,8 @@ k_corr_tiles(const double* __restrict__ z, const int32_t* __restrict__ n_nodes,
         const bool in0 = gj < N, in1 = gj + 1 < N;
         // an element counts when it is strictly above the diagonal; it stands for (i,j) and (j,i)
         const bool up0 = in0 && (!diag_tile || gj > gi), up1 = in1 && (!diag_tile || gj + 1 > gi);
-        if (up0 && v0 >= 0.0 && v0 > rc) { lsum += v0; lcnt += 1.0; }
-        if (up1 && v1 >= 0.0 && v1 > rc) { lsum += v1; lcnt += 1.0; }
+        if (up0 && v0 > rc) { lsum += v0; lcnt += 1.0; }
+        if (up1 && v1 > rc) { lsum += v1; lcnt += 1.0; }
         if (Rb) {
           if (diag_tile) {
             if (in0 && gj == gi) Rb[(size_t)gi * ldn + gj] = sie_nan();
