@@ -200,6 +200,42 @@ def fp64_gemm_peak(torch):
     return best
 
 
+def corr_25km(torch, fp64_peak, world, rank):
+    """BASELINE.json's second figure: all-pairs correlation + tau on the 25 km 448x304 grid (configs[3]), R not stored,
+    tile rows sharded over the ranks (`sie_corr_tau(shard_rank, shard_count)`); TFLOP/s of the upper-triangle
+    algorithmic work N(N+1)T against the FP64 tensor peak measured above.  Timed on the device, rank 0's shard."""
+    from seaiceextentforecasting_b200 import synthetic as syn
+    from seaiceextentforecasting_b200.engine import NetworkBatch, h2d, r_crit_ttest
+    X, Y, T = 448, 304, 42
+    data, _ = syn.make_field(X, Y, T, 7, n_modes=200)
+    n_upper = int((~np.isnan(data).any(axis=2)).sum())
+    eng = NetworkBatch(X, Y, T, 1, latlon=False, n_upper=n_upper, keep_R=False, max_areas=8)
+    fields = h2d(data.reshape(1, X * Y, T))
+    jf = torch.zeros(1, dtype=torch.int32, device="cuda")
+    jT = torch.full((1,), T, dtype=torch.int32, device="cuda")
+    rc = h2d(np.array([r_crit_ttest(T, 0.01)]))
+    eng.detrend_zscore(fields, jf, jT, True)
+    for _ in range(3):
+        eng.corr_tau(rc, store_R=False, shard_rank=rank, shard_count=world)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        eng.corr_tau(rc, store_R=False, shard_rank=rank, shard_count=world)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    N = int(eng.n_nodes.item())
+    flop = N * (N + 1.0) * T / world
+    tf = flop / (ms * 1e-3) / 1e12
+    del eng
+    torch.cuda.empty_cache()
+    return {"workload": f"448x304 grid, {N} nodes, T={T}, R not stored, row shard {rank}/{world}", "ms": ms,
+            "tflops_fp64": tf, "peak_tflops_fp64": fp64_peak, "frac": tf / fp64_peak if fp64_peak else None,
+            "flop_model": "N(N+1)T per network (upper triangle), split evenly over the shards"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -307,7 +343,8 @@ def run_ours(args):
     detr_bytes = float((16 * cells * T).sum())
     kern = {
         "sic.detrend_zscore": {"bound": "hbm", "work": detr_bytes + float((8 * N * sw.sic.Tp).sum())},
-        "sic.corr_tau": {"bound": "tensor", "work": corr_flop, "bytes": corr_bytes},
+        # R is materialised here (8 N^2 bytes per network against N(N+1)T flop, T <= 42 -> <= 5.3 flop/B): HBM-store bound
+        "sic.corr_tau": {"bound": "hbm", "work": corr_bytes + float((8 * N * sw.sic.Tp).sum()), "flop": corr_flop},
         "sic.area_level": {"bound": "hbm", "work": 8.0 * area_work},
     }
     top = max((k for k in stage_ms), key=lambda k: stage_ms[k])
@@ -322,6 +359,8 @@ def run_ours(args):
             ach = k["work"] / (ms * 1e-3) / 1e9
             roof[name] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                           "traffic": None, "ms": ms, "peak_source": hbm_src}
+            if "flop" in k:
+                roof[name]["tflops_fp64"] = k["flop"] / (ms * 1e-3) / 1e12
         else:
             ach = k["work"] / (ms * 1e-3) / 1e12
             roof[name] = {"bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -338,6 +377,7 @@ def run_ours(args):
         pass
     main_roof = dict(roof.get(top, roof.get("sic.area_level", {})))
     main_roof["kernel"] = top
+    corr25 = corr_25km(torch, fp64_peak, world, rank) if args.corr25 else None
 
     if rank == 0:
         line = {
@@ -356,6 +396,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": main_roof,
             "roofline_all": roof,
+            "corr_25km": corr25,
             "stage_ms": stage_ms,
             "gp_failures": bad,
             "checks": {"forecasts_per_rank": sw.n_forecasts, "areas_mean": float(sw.sic.n_areas.cpu().numpy().mean())},
@@ -377,6 +418,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-corr25", dest="corr25", action="store_false",
+                    help="skip the 25 km all-pairs correlation probe (second half of BASELINE.json's metric)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
