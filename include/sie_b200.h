@@ -170,6 +170,15 @@ int sie_gp_forecast(const SieGpProblem* prob, int P, const double* y_all,
                     int max_pred, SieGpResult* out, void* scratch, size_t scratch_bytes, void* stream);
 size_t sie_gp_scratch_bytes(int P, int max_pred, int max_n);
 
+/* Hyper-parameter grid (the search the reference leaves commented out at north/June1st.py:259-262, done over the
+ * `ls` x `ss` grids of :210-211): problem p fixes (network set, region, l = prob[p].ell); Sigma~ = expm(l M) and
+ * W = X Sigma~ X^T are built once and the fit / nlML (MLII :235-257) is evaluated for every sig_grid[k].
+ * prob[p].sig is ignored.  out [P][n_sig].  Same scratch as sie_gp_forecast. */
+int sie_gp_hyper_grid(const SieGpProblem* prob, int P, const double* sig_grid, int n_sig, const double* y_all,
+                      const double* anom_sic, const int32_t* n_areas_sic, int max_areas_sic, int Tstride_sic,
+                      const double* anom_sst, const int32_t* n_areas_sst, int max_areas_sst, int Tstride_sst,
+                      int max_pred, SieGpResult* out, void* scratch, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,8 @@ _SIGS = {
     "sie_gp_forecast": (C.c_int, [c_p, C.c_int, c_p, c_p, c_p, C.c_int, C.c_int, c_p, c_p, C.c_int, C.c_int,
                                   C.c_int, c_p, c_p, c_sz, c_p]),
     "sie_gp_scratch_bytes": (c_sz, [C.c_int, C.c_int, C.c_int]),
+    "sie_gp_hyper_grid": (C.c_int, [c_p, C.c_int, c_p, C.c_int, c_p, c_p, c_p, C.c_int, C.c_int, c_p, c_p, C.c_int,
+                                    C.c_int, C.c_int, c_p, c_p, c_sz, c_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -503,7 +503,12 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
               const double* __restrict__ anom_sic, const int32_t* __restrict__ n_areas_sic, int ma_sic, int ts_sic,
               const double* __restrict__ anom_sst, const int32_t* __restrict__ n_areas_sst, int ma_sst, int ts_sst,
               int max_pred, SieGpResult* __restrict__ out, unsigned char* __restrict__ scratch, size_t per_cta,
-              const int32_t* __restrict__ order, int* __restrict__ queue) {
+              const int32_t* __restrict__ order, int* __restrict__ queue, const double* __restrict__ sig_grid,
+              int n_sig) {
+  // hyper-parameter grid mode (sig_grid != nullptr): problem p is one (network set, region, l); Sigma~ = expm(l M) and
+  // W = X Sigma~ X^T are built once and the Cholesky fit / nlML is repeated for the n_sig noise values; results go to
+  // out[p * n_sig + k].  Otherwise n_sig = 1, sigma_n~ = prob[p].sig and the result goes to out[p].
+  const int ns = sig_grid ? n_sig : 1;
   extern __shared__ __align__(16) unsigned char smraw[];
   Smem& sm = *reinterpret_cast<Smem*>(smraw);
   const int tid = threadIdx.x;
@@ -537,7 +542,7 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
     const long long clk_start = clock64();
     __syncthreads();
     if (n < 2 || n + 1 > MAXN) {
-      if (tid == 0) { res.info = -2; out[p] = res; }
+      if (tid == 0) { res.info = -2; for (int k = 0; k < ns; ++k) out[(size_t)p * ns + k] = res; }
       continue;
     }
     const int na1 = n_areas_sic[pr.job_sic];
@@ -592,7 +597,7 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
     const int np_ = sm.misc[0];
     res.n_pred = np_;
     if (np_ == 0 || np_ > ld) {
-      if (tid == 0) { res.info = (np_ == 0) ? -1 : -2; out[p] = res; }
+      if (tid == 0) { res.info = (np_ == 0) ? -1 : -2; for (int k = 0; k < ns; ++k) out[(size_t)p * ns + k] = res; }
       continue;
     }
     // ---- X (n+1 rows) with optional column z-score over all n+1 rows (:226-227)
@@ -658,19 +663,29 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
       sm.u.gp.W[i * LDS + jj] = sacc;
     }
     __syncthreads();
+    if (pr.want_grad) {        // sigma-independent part of the MLII gradient: X (M Sigma~) (:248)
+      cta_gemm(buf[5], ld, M, ld, E, ld, np_, np_, np_, sm);
+      cta_gemm(XM, ld, Xg, ld, buf[5], ld, n, np_, np_, sm);
+    }
+    for (int ks = 0; ks < ns; ++ks) {
+    const double sig = sig_grid ? sig_grid[ks] : pr.sig;
+    SieGpResult* const outp = out + (size_t)p * ns + ks;
+    res.fmean = res.fvar = res.sigma_f = res.nlml = res.g_ell = res.g_sig = sie_nan();
+    res.info = 0;
+    __syncthreads();
     // ---- L~ = chol(W + sig I); A~ ; sigma_f = y^T A~ / n  (:265-267)
     for (int idx = tid; idx < n * n; idx += GT) {
       const int i = idx / n, jj = idx - i * n;
-      sm.u.gp.K[i * LDS + jj] = sm.u.gp.W[i * LDS + jj] + ((i == jj) ? pr.sig : 0.0);
+      sm.u.gp.K[i * LDS + jj] = sm.u.gp.W[i * LDS + jj] + ((i == jj) ? sig : 0.0);
     }
     __syncthreads();
     int info = cta_cholesky(sm.u.gp.K, n, sm);
-    if (info) { if (tid == 0) { res.info = info; out[p] = res; } continue; }
+    if (info) { if (tid == 0) { res.info = info; res.cycles_total = clock64() - clk_start; *outp = res; } continue; }
     cta_chol_solve(sm.u.gp.K, n, sm.y, sm.ya, sm.v);
     double sf = 0.0;
     for (int t = 0; t < n; ++t) sf = fma(sm.y[t], sm.ya[t], sf);
     sf /= (double)n;
-    const double sn = sf * pr.sig;
+    const double sn = sf * sig;
     res.sigma_f = sf;
     __syncthreads();
     // ---- L = chol(sf*W + sn I); alpha (:269-271)
@@ -680,7 +695,7 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
     }
     __syncthreads();
     info = cta_cholesky(sm.u.gp.K, n, sm);
-    if (info) { if (tid == 0) { res.info = info; out[p] = res; } continue; }
+    if (info) { if (tid == 0) { res.info = info; res.cycles_total = clock64() - clk_start; *outp = res; } continue; }
     cta_chol_solve(sm.u.gp.K, n, sm.y, sm.alpha, sm.v);
     // ---- predictive mean / variance (:272-277)
     for (int i = tid; i < n; i += GT) {
@@ -722,10 +737,7 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
     res.fmean = sm.dmisc[0]; res.fvar = sm.dmisc[1]; res.nlml = sm.dmisc[2];
     // ---- MLII gradient as written at :248-252
     if (pr.want_grad) {
-      // dKdl = X (M Sigma) X^T + sn I, Sigma = sf * E
-      double* MS = buf[5];
-      cta_gemm(MS, ld, M, ld, E, ld, np_, np_, np_, sm);
-      cta_gemm(XM, ld, Xg, ld, MS, ld, n, np_, np_, sm);
+      // dKdl = X (M Sigma) X^T + sn I, Sigma = sf * E  (XM = X M Sigma~ was formed before the sigma loop)
       for (int which = 0; which < 2; ++which) {
         for (int idx = tid; idx < n * n; idx += GT) {
           const int i = idx / n, jj = idx - i * n;
@@ -769,7 +781,8 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
         __syncthreads();
       }
     }
-    if (tid == 0) { res.cycles_total = clock64() - clk_start; out[p] = res; }
+    if (tid == 0) { res.cycles_total = clock64() - clk_start; *outp = res; }
+    }   // sigma loop
   }
 }
 
@@ -827,11 +840,10 @@ extern "C" size_t sie_gp_scratch_bytes(int P, int max_pred, int max_n) {
   return gp_header_bytes(P) + (size_t)gp_grid(P) * gp_per_cta_bytes(max_pred);
 }
 
-extern "C" int sie_gp_forecast(const SieGpProblem* prob, int P, const double* y_all, const double* anom_sic,
-                               const int32_t* n_areas_sic, int max_areas_sic, int Tstride_sic,
-                               const double* anom_sst, const int32_t* n_areas_sst, int max_areas_sst,
-                               int Tstride_sst, int max_pred, SieGpResult* out, void* scratch,
-                               size_t scratch_bytes, void* stream) {
+static int gp_launch(const SieGpProblem* prob, int P, const double* y_all, const double* anom_sic,
+                     const int32_t* n_areas_sic, int max_areas_sic, int Tstride_sic, const double* anom_sst,
+                     const int32_t* n_areas_sst, int max_areas_sst, int Tstride_sst, int max_pred, SieGpResult* out,
+                     void* scratch, size_t scratch_bytes, const double* sig_grid, int n_sig, void* stream) {
   SIE_CHECK_ARG(prob && y_all && anom_sic && n_areas_sic && out && scratch, "null pointer");
   SIE_CHECK_ARG(P > 0 && max_pred > 0 && (max_pred % 4) == 0, "P>0 and max_pred a positive multiple of 4");
   const size_t per = gp_per_cta_bytes(max_pred);
@@ -850,7 +862,26 @@ extern "C" int sie_gp_forecast(const SieGpProblem* prob, int P, const double* y_
   cudaFuncSetAttribute(k_gp_forecast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_gp_forecast<<<grid, GT, smem, st>>>(prob, P, y_all, anom_sic, n_areas_sic, max_areas_sic, Tstride_sic, anom_sst,
                                         n_areas_sst, max_areas_sst, Tstride_sst, max_pred, out,
-                                        (unsigned char*)scratch + head, per, order, queue);
+                                        (unsigned char*)scratch + head, per, order, queue, sig_grid, n_sig);
   SIE_CHECK_LAUNCH();
   return SIE_OK;
+}
+
+extern "C" int sie_gp_forecast(const SieGpProblem* prob, int P, const double* y_all, const double* anom_sic,
+                               const int32_t* n_areas_sic, int max_areas_sic, int Tstride_sic,
+                               const double* anom_sst, const int32_t* n_areas_sst, int max_areas_sst,
+                               int Tstride_sst, int max_pred, SieGpResult* out, void* scratch,
+                               size_t scratch_bytes, void* stream) {
+  return gp_launch(prob, P, y_all, anom_sic, n_areas_sic, max_areas_sic, Tstride_sic, anom_sst, n_areas_sst,
+                   max_areas_sst, Tstride_sst, max_pred, out, scratch, scratch_bytes, nullptr, 1, stream);
+}
+
+extern "C" int sie_gp_hyper_grid(const SieGpProblem* prob, int P, const double* sig_grid, int n_sig,
+                                 const double* y_all, const double* anom_sic, const int32_t* n_areas_sic,
+                                 int max_areas_sic, int Tstride_sic, const double* anom_sst,
+                                 const int32_t* n_areas_sst, int max_areas_sst, int Tstride_sst, int max_pred,
+                                 SieGpResult* out, void* scratch, size_t scratch_bytes, void* stream) {
+  SIE_CHECK_ARG(sig_grid && n_sig > 0, "sig_grid must hold n_sig > 0 values");
+  return gp_launch(prob, P, y_all, anom_sic, n_areas_sic, max_areas_sic, Tstride_sic, anom_sst, n_areas_sst,
+                   max_areas_sst, Tstride_sst, max_pred, out, scratch, scratch_bytes, sig_grid, n_sig, stream);
 }

@@ -119,39 +119,37 @@ class GpBatch:
             self.max_pred, _ptr(out[p0 * osz:]), _ptr(self.scratch), self.scratch_bytes, _stream())
         _lib.check(rc, "sie_gp_forecast")
 
+    def run_grid(self, prob_dev, sig_grid_dev, n_sig, y_dev, sic, sst, out):
+        """Hyper-parameter grid: problem p fixes l = prob[p].ell; every sig_grid[k] is evaluated from the same
+        expm / X Sigma X^T (sie_gp_hyper_grid).  `out`: uint8 device buffer of P * n_sig result records."""
+        rc = self.lib.sie_gp_hyper_grid(
+            _ptr(prob_dev), self.P, _ptr(sig_grid_dev), int(n_sig), _ptr(y_dev), _ptr(sic.anomaly), _ptr(sic.n_areas),
+            sic.MA, sic.Tstride, _ptr(sst.anomaly) if sst is not None else C.c_void_p(0),
+            _ptr(sst.n_areas) if sst is not None else C.c_void_p(0), sst.MA if sst is not None else 0,
+            sst.Tstride if sst is not None else 0, self.max_pred, _ptr(out), _ptr(self.scratch), self.scratch_bytes,
+            _stream())
+        _lib.check(rc, "sie_gp_hyper_grid")
+
     def results(self):
         return self.out.cpu().numpy().view(GP_RESULT_DTYPE)
 
 
-def forecast(y, anoms_sic, anoms_sst=None, rule=0, alpha=0.05, zscore=False, ell=1.0, sig=1.0, want_grad=False):
-    """One GP forecast from node series given as dicts (the reference's `dataset['anoms']`), i.e. the body of
-    `forecast()` for one region (north/June1st.py:214-277).  Returns the raw result record."""
-    require_cuda()
-    y = np.asarray(y, dtype=np.float64).reshape(-1)
-    n = y.size
+class _SeriesSet:
+    """Node series of ONE network given as a dict (the reference's `dataset['anoms']`), packed the way GpBatch reads a
+    NetworkBatch: anomaly [1][nA][n+1], n_areas [1]."""
 
-    def pack(anoms):
+    def __init__(self, anoms, n):
         keys = list(anoms)
         arr = np.zeros((1, max(1, len(keys)), n + 1))
         for a, k in enumerate(keys):
             arr[0, a] = np.asarray(anoms[k], dtype=np.float64)[:n + 1]
-        return arr, len(keys)
+        self.anomaly = h2d(arr)
+        self.n_areas = torch.tensor([len(keys)], dtype=torch.int32, device="cuda")
+        self.MA = arr.shape[1]
+        self.Tstride = n + 1
 
-    class _Set:   # minimal stand-in exposing what GpBatch.run reads
-        pass
 
-    sets = []
-    for anoms in (anoms_sic, anoms_sst):
-        if anoms is None:
-            sets.append(None)
-            continue
-        arr, na = pack(anoms)
-        s = _Set()
-        s.anomaly = h2d(arr)
-        s.n_areas = torch.tensor([na], dtype=torch.int32, device="cuda")
-        s.MA = arr.shape[1]
-        s.Tstride = n + 1
-        sets.append(s)
+def _one_problem(n, anoms_sst, rule, alpha, zscore, want_grad):
     prob = np.zeros(1, dtype=GP_PROBLEM_DTYPE)
     prob["job_sic"] = 0
     prob["job_sst"] = 0 if anoms_sst is not None else -1
@@ -160,12 +158,48 @@ def forecast(y, anoms_sic, anoms_sst=None, rule=0, alpha=0.05, zscore=False, ell
     prob["zscore"] = int(zscore)
     prob["want_grad"] = int(want_grad)
     prob["r_sel"] = r_crit_pearson(n, alpha) if rule == RULE_POS_SIG else 0.0
+    return prob
+
+
+def forecast(y, anoms_sic, anoms_sst=None, rule=0, alpha=0.05, zscore=False, ell=1.0, sig=1.0, want_grad=False):
+    """One GP forecast from node series given as dicts (the reference's `dataset['anoms']`), i.e. the body of
+    `forecast()` for one region (north/June1st.py:214-277).  Returns the raw result record."""
+    require_cuda()
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    n = y.size
+    s1 = _SeriesSet(anoms_sic, n)
+    s2 = _SeriesSet(anoms_sst, n) if anoms_sst is not None else None
+    prob = _one_problem(n, anoms_sst, rule, alpha, zscore, want_grad)
     prob["ell"] = ell
     prob["sig"] = sig
-    npred = sets[0].MA + (sets[1].MA if sets[1] is not None else 0)
+    npred = s1.MA + (s2.MA if s2 is not None else 0)
     gp = GpBatch(1, max_pred=max(4, npred))
-    gp.run(h2d(prob.view(np.uint8)), h2d(y), sets[0], sets[1])
+    gp.run(h2d(prob.view(np.uint8)), h2d(y), s1, s2)
     return gp.results()[0]
+
+
+def hyper_grid(y, anoms_sic, anoms_sst=None, rule=0, alpha=0.05, zscore=False, ells=None, sigs=None, want_grad=False):
+    """Grid search over the reference's hyper-parameter grids `ls = np.logspace(-7,2,20)`, `ss = np.logspace(-3,9,20)`
+    (north/June1st.py:210-211; the `minimize(MLII, ...)` call at :259-262 is commented out there): negative log marginal
+    likelihood of MLII() for every (l, sigma_n~) pair, one expm per l.
+    Returns (records [len(ells)][len(sigs)], (i, j) of the smallest finite nlML)."""
+    require_cuda()
+    ells = np.logspace(-7, 2, 20) if ells is None else np.asarray(ells, dtype=np.float64)
+    sigs = np.logspace(-3, 9, 20) if sigs is None else np.asarray(sigs, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    n = y.size
+    s1 = _SeriesSet(anoms_sic, n)
+    s2 = _SeriesSet(anoms_sst, n) if anoms_sst is not None else None
+    prob = np.repeat(_one_problem(n, anoms_sst, rule, alpha, zscore, want_grad), len(ells))
+    prob["ell"] = ells
+    npred = s1.MA + (s2.MA if s2 is not None else 0)
+    gp = GpBatch(len(ells), max_pred=max(4, npred))
+    out = torch.empty(len(ells) * len(sigs) * GP_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    gp.run_grid(h2d(prob.view(np.uint8)), h2d(sigs), len(sigs), h2d(y), s1, s2, out)
+    rec = out.cpu().numpy().view(GP_RESULT_DTYPE).reshape(len(ells), len(sigs))
+    nl = np.where((rec["info"] == 0) & np.isfinite(rec["nlml"]), rec["nlml"], np.inf)
+    best = np.unravel_index(int(np.argmin(nl)), nl.shape)
+    return rec, (int(best[0]), int(best[1]))
 
 
 def mlii(theta, y, anoms_sic, anoms_sst=None, rule=0, alpha=0.05, zscore=False):
@@ -446,6 +480,24 @@ class RetrospectiveSweep:
         self.gp.run(d["prob"], d["y"], self.sic, self.sst, (0, self.pB))
         mark("gpB")
         main.wait_stream(sA)                    # the step is complete on `main` once wave A's GP has finished too
+
+    def hyper_grid(self, ells=None, sigs=None):
+        """BASELINE.json configs[4] on this member: every GP problem of the sweep (year x init x region) evaluated on
+        the reference's `ls` x `ss` hyper-parameter grid (north/June1st.py:210-211), from the node series the last
+        compute() left on the device.  One CTA per (problem, l): expm and X Sigma X^T once, the Cholesky fit / nlML for
+        every sigma.  Returns records [P][len(ells)][len(sigs)] (host)."""
+        ells = np.logspace(-7, 2, 20) if ells is None else np.asarray(ells, dtype=np.float64)
+        sigs = np.logspace(-3, 9, 20) if sigs is None else np.asarray(sigs, dtype=np.float64)
+        nl, ns = len(ells), len(sigs)
+        if getattr(self, "_grid", None) is None or self._grid[0] != (nl, ns):
+            prob = np.repeat(self.plan.prob, nl)
+            gp = GpBatch(self.P * nl, max_pred=self.gp.max_pred)
+            out = torch.empty(self.P * nl * ns * GP_RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+            self._grid = ((nl, ns), gp, out, prob)
+        _, gp, out, prob = self._grid
+        prob["ell"] = np.tile(ells, self.P)
+        gp.run_grid(h2d(prob.view(np.uint8)), h2d(sigs), ns, self.dev["y"], self.sic, self.sst, out)
+        return out.cpu().numpy().view(GP_RESULT_DTYPE).reshape(self.P, nl, ns)
 
     def kernel_launches(self):
         """Kernels of libsie_b200 enqueued by one compute(): 12 per network batch (K1: 3, K2: 4, K3-K5: 2, K6: 3), per

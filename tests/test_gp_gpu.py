@@ -96,3 +96,47 @@ def test_not_spd_reports_like_reference(lib_built):
     assert r["info"] > 0 or not np.isfinite(r["fmean"])
     nl, g = mlii(np.array([np.log(1e-3), -800.0]), y, sic, rule=RULE_ALL)
     assert nl == np.inf or np.isfinite(nl)
+
+
+@pytest.mark.parametrize("name,k", [("north_june", 0), ("north_august", 1), ("south_february", 2)])
+def test_hyper_grid_matches_oracle(lib_built, name, k):
+    """sie_gp_hyper_grid: the 20 x 20 (l, sigma_n~) grid of north/June1st.py:210-211, one expm per l, against MLII()
+    of the oracle evaluated pair by pair (value and, for the June case, the gradient as written)."""
+    from oracle import gp as og
+    from seaiceextentforecasting_b200.forecast import hyper_grid
+    cfg = CONFIGS[name]
+    n = 20
+    y, sic, sst = make_problem(77 + k, n, nA=10, nS=4 if cfg.use_sst else 0, scale=1.0 if cfg.zscore else 30.0)
+    ells, sigs = np.logspace(-7, 2, 20), np.logspace(-3, 9, 20)
+    want_grad = name == "north_june"
+    rec, best = hyper_grid(y, sic, sst, rule=cfg.rule[k], alpha=cfg.alpha, zscore=cfg.zscore, ells=ells, sigs=sigs,
+                           want_grad=want_grad)
+    assert rec.shape == (20, 20)
+    Xfull = og.select_predictors(y, sic, sst, {RULE_POS: "pos", RULE_ALL: "all", RULE_POS_SIG: "pos_sig"}[cfg.rule[k]],
+                                 cfg.alpha)
+    X, Xs, M = og.design(Xfull, cfg.zscore)
+    from scipy.linalg import expm
+    ref = np.full((20, 20), np.inf)
+    checked = 0
+    for i, ell in enumerate(ells):
+        E = expm(ell * M)
+        for j, sig in enumerate(sigs):
+            val, grad = og.mlii(np.log([ell, sig]), X, y[:, None], M)
+            r = rec[i, j]
+            if not np.isfinite(val):
+                assert r["info"] != 0
+                continue
+            ref[i, j] = val
+            assert r["info"] == 0 and r["n_pred"] == Xfull.shape[1]
+            sf = r["sigma_f"]
+            cond = np.linalg.cond(sf * (X @ E @ X.T + sig * np.eye(n)))
+            t = tol(r, cond)
+            assert abs(r["nlml"] - val) <= t * max(1.0, abs(val)), (i, j, r["nlml"], val, t)
+            if want_grad and cond < 1e8:
+                assert abs(r["g_ell"] - grad[0]) <= 10 * t * max(1.0, abs(grad[0])), (i, j, r["g_ell"], grad[0])
+                assert abs(r["g_sig"] - grad[1]) <= 10 * t * max(1.0, abs(grad[1])), (i, j, r["g_sig"], grad[1])
+            checked += 1
+    assert checked > 300
+    # the grid minimum agrees wherever it is not a numerical tie
+    ob = np.unravel_index(int(np.argmin(ref)), ref.shape)
+    assert abs(ref[best] - ref[ob]) <= 1e-9 * max(1.0, abs(ref[ob]))

@@ -99,3 +99,33 @@ def test_multi_init_north_sweep_matches_oracle(lib_built):
                     ref = ora[cfg.name][reg + suf][i]
                     got = out[cfg.name][reg + "_raw" + suf][i]
                     assert abs(got - ref) <= 50 * gp_tol(rec) * max(abs(ref), 1e-2), (cfg.name, reg, year, got, ref)
+
+
+def test_sweep_hyper_grid_contains_the_script_settings(lib_built):
+    """configs[4]: the whole sweep on the 20 x 20 hyper-parameter grid.  The scripts' own (l, sigma) settings are grid
+    points (`ls[16], ss[1]` ... north/June1st.py:210-213), so those grid entries must reproduce the forecasts."""
+    import bench
+    from seaiceextentforecasting_b200.config import CONFIGS
+    from seaiceextentforecasting_b200.forecast import RetrospectiveSweep
+    w = bench.make_workload(3)
+    names = ["north_june", "north_september"]
+    sw = RetrospectiveSweep(names, {n: w["sic"][n] for n in names}, w["sie"], 2012, 2020, w["psar"], w["sst"], w["lat"])
+    sw.run()
+    raw = sw.raw.copy()
+    ells, sigs = np.logspace(-7, 2, 20), np.logspace(-3, 9, 20)
+    grid = sw.hyper_grid(ells, sigs)
+    assert grid.shape == (sw.P, 20, 20)
+    hits = 0
+    for p, (ci, k, year) in enumerate(sw.plan.prob_meta):
+        cfg = sw.cfgs[ci]
+        i = int(np.argmin(np.abs(np.log(ells) - np.log(cfg.ell[k]))))
+        j = int(np.argmin(np.abs(np.log(sigs) - np.log(cfg.sig[k]))))
+        if not (np.isclose(ells[i], cfg.ell[k], rtol=1e-12) and np.isclose(sigs[j], cfg.sig[k], rtol=1e-12)):
+            continue
+        g, r = grid[p, i, j], raw[p]
+        assert g["info"] == r["info"] and g["n_pred"] == r["n_pred"]
+        if r["info"] == 0:
+            for key in ("fmean", "fvar", "sigma_f", "nlml"):
+                assert abs(g[key] - r[key]) <= 1e-9 * max(1.0, abs(r[key])), (p, key, g[key], r[key])
+        hits += 1
+    assert hits >= sw.P // 2
