@@ -179,6 +179,25 @@ int sie_gp_hyper_grid(const SieGpProblem* prob, int P, const double* sig_grid, i
                       const double* anom_sst, const int32_t* n_areas_sst, int max_areas_sst, int Tstride_sst,
                       int max_pred, SieGpResult* out, void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Ingest (the steps immediately before the hot path).
+ * Replaces: readNSIDC                                          north/September1st.py:72-139
+ *
+ * sie_nsidc_monthly   files [n_files][file_stride] raw NSIDC .bin images (300-byte header + C bytes, :93-104/:121-127)
+ *                     -> monthly [C] = nanmean over the files of byte/250, values > 1 (flags) -> NaN (:128)
+ * sie_polar_hole_fill phole = nanmean(monthly[hole-0.5 < lat < hole]); filled = where(lat >= hole-0.5, phole, monthly)
+ *                     (:129-136); scratch [C] doubles; phole is also returned through *phole (device)
+ * sie_regrid_linear   scipy griddata(..., 'linear') (:137-138) as a 3-nnz-per-row SpMV: vert [Ct][3] source cells of
+ *                     the enclosing Delaunay triangle (-1 = outside the hull -> NaN), bary [Ct][3] barycentric
+ *                     weights; src [F][C] -> dst [F][Ct]
+ */
+int sie_nsidc_monthly(const uint8_t* files, int n_files, size_t file_stride, int header_bytes, int C,
+                      double* monthly, void* stream);
+int sie_polar_hole_fill(const double* monthly, const double* lat, double hole, int C, double* filled,
+                        double* phole, double* scratch, void* stream);
+int sie_regrid_linear(const double* src, int F, int C, const int32_t* vert, const double* bary, int Ct,
+                      double* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

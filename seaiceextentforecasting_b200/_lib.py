@@ -47,6 +47,9 @@ _SIGS = {
     "sie_gp_forecast": (C.c_int, [c_p, C.c_int, c_p, c_p, c_p, C.c_int, C.c_int, c_p, c_p, C.c_int, C.c_int,
                                   C.c_int, c_p, c_p, c_sz, c_p]),
     "sie_gp_scratch_bytes": (c_sz, [C.c_int, C.c_int, C.c_int]),
+    "sie_nsidc_monthly": (C.c_int, [c_p, C.c_int, c_sz, C.c_int, C.c_int, c_p, c_p]),
+    "sie_polar_hole_fill": (C.c_int, [c_p, c_p, C.c_double, C.c_int, c_p, c_p, c_p, c_p]),
+    "sie_regrid_linear": (C.c_int, [c_p, C.c_int, C.c_int, c_p, c_p, C.c_int, c_p, c_p]),
     "sie_gp_hyper_grid": (C.c_int, [c_p, C.c_int, c_p, C.c_int, c_p, c_p, c_p, C.c_int, C.c_int, c_p, c_p, C.c_int,
                                     C.c_int, C.c_int, c_p, c_p, c_sz, c_p]),
 }

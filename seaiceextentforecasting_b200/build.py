@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsie_b200.so")
-SOURCES = ["abi.cu", "detrend.cu", "corr.cu", "area.cu", "links.cu", "gp.cu"]
+SOURCES = ["abi.cu", "detrend.cu", "corr.cu", "area.cu", "links.cu", "gp.cu", "ingest.cu"]
 NVCC_FLAGS = (["-DSIE_AREA_DEBUG_ROUNDS"] if os.environ.get("SIE_DEBUG") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 
