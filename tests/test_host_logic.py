@@ -130,3 +130,58 @@ def test_two_rank_gather_assembles_full_sweep():
     for p in procs:
         p.join(timeout=60)
     assert ok
+
+
+def test_retro_csv_layout_matches_reference_script():
+    """the CSV tables of June1st_retro.py:344-364, rebuilt from SweepPlan.assemble() output,
+    against a literal restatement of those lines (prep/zip/DataFrame) on the same numbers."""
+    import pandas as pd
+    from seaiceextentforecasting_b200 import report
+    from seaiceextentforecasting_b200.config import CONFIGS
+    from seaiceextentforecasting_b200.forecast import GP_RESULT_DTYPE, SweepPlan
+    rng = np.random.default_rng(5)
+    T = 2020 - 1979 + 1
+    sie = {r: np.round(6 - 0.05 * np.arange(T) + 0.4 * rng.standard_normal(T), 3) for r in CONFIGS["north_june"].regions}
+    plan = SweepPlan(["north_june"], sie, 2010, 2020)
+    raw = np.zeros(plan.P, dtype=GP_RESULT_DTYPE)
+    raw["fmean"] = rng.standard_normal(plan.P)
+    raw["fvar"] = rng.uniform(0.01, 0.5, plan.P)
+    gpr = plan.assemble(raw)
+    df_dt, df_rt = report.retro_tables(plan, gpr, "north_june")
+    # --- literal restatement of June1st_retro.py:293-361 on the same arrays
+    fmin, fmax = 2010, 2020
+    GPR, SIEs, SIEs_dt = gpr["north_june"], plan.sie, plan.sie_dt
+    regions = ['Pan-Arctic', 'Beaufort', 'Chukchi']
+    skill_rt, skill_dt, dt_obs = [], [], []
+    for k in range(3):
+        dt = [SIEs_dt[regions[k]][t - (fmin - 1), t - 1979] for t in range(fmin, fmax + 1)]
+        dt_obs.append(dt)
+        forecast_rt = GPR[regions[k] + '_fmean_rt']
+        obs_rt = SIEs[regions[k]][fmin - 1979:]
+        a = np.mean((obs_rt - forecast_rt) ** 2)
+        b = np.mean((obs_rt - np.nanmean(obs_rt)) ** 2)
+        skill_rt.append((1 - (a / b)).round(3))
+        c = np.mean((dt - GPR[regions[k] + '_fmean']) ** 2)
+        d = np.mean((dt - np.nanmean(dt)) ** 2)
+        skill_dt.append((1 - (c / d)).round(3))
+    years = np.arange(fmin, fmax + 1).tolist()
+    years.append('Skill')
+
+    def prep(data, skill=None):
+        if type(data) != list:
+            data = data.tolist()
+        data.append(skill if skill is not None else '')
+        return data
+    columns1 = ['Pan-Arctic$_o$', 'Pan-Arctic$_f$', 'Pan-Arctic$_f$ unc', 'Beaufort$_o$', 'Beaufort$_f$', 'Beaufort$_f$ unc',
+                'Chukchi$_o$', 'Chukchi$_f$', 'Chukchi$_f$ unc']
+    columns2 = ['Pan-Arctic$_o$', 'Pan-Arctic$_f$', 'Beaufort$_o$', 'Beaufort$_f$', 'Chukchi$_o$', 'Chukchi$_f$']
+    data_dt = list(zip(prep(dt_obs[0]), prep(GPR['Pan-Arctic_fmean'], skill_dt[0]), prep(np.sqrt(GPR['Pan-Arctic_fvar']).round(3)),
+                       prep(dt_obs[1]), prep(GPR['Beaufort_fmean'], skill_dt[1]), prep(np.sqrt(GPR['Beaufort_fvar']).round(3)),
+                       prep(dt_obs[2]), prep(GPR['Chukchi_fmean'], skill_dt[2]), prep(np.sqrt(GPR['Chukchi_fvar']).round(3))))
+    ref_dt = pd.DataFrame(data_dt, index=years, columns=columns1)
+    data_rt = list(zip(prep(SIEs['Pan-Arctic'][fmin - 1979:]), prep(GPR['Pan-Arctic_fmean_rt'], skill_rt[0]),
+                       prep(SIEs['Beaufort'][fmin - 1979:]), prep(GPR['Beaufort_fmean_rt'], skill_rt[1]),
+                       prep(SIEs['Chukchi'][fmin - 1979:]), prep(GPR['Chukchi_fmean_rt'], skill_rt[2])))
+    ref_rt = pd.DataFrame(data_rt, index=years, columns=columns2)
+    assert df_dt.equals(ref_dt) and df_rt.equals(ref_rt)
+    assert list(df_dt.index) == years and list(df_dt.columns) == columns1
