@@ -451,11 +451,15 @@ class RetrospectiveSweep:
             mark("gp")
             return
         if self._streams is None:
-            self._streams = [torch.cuda.Stream(priority=-1) for _ in range(3)]
-        sA, sSb, sSa = self._streams
+            self._streams = [torch.cuda.Stream(priority=-1) for _ in range(4)]
+        sA, sSb, sSa, sB = self._streams
         nJ, nS = self.sic.B, (self.sst.B if self.sst is not None else 0)
         for st in self._streams:
             st.wait_stream(main)
+        # enqueue order = issue order: the long-window SIC chain (the critical path) goes first; all four chains have the
+        # same priority (measured: 14.3 ms against 15.1 ms with the short-window chain first)
+        with torch.cuda.stream(sB):
+            chain("sicB", self.sic, d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"], (0, self.jB))
         with torch.cuda.stream(sA):            # wave A: short windows -> the big GP problems
             chain("sicA", self.sic, d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"], (self.jB, nJ))
         if self.sst is not None:
@@ -463,7 +467,7 @@ class RetrospectiveSweep:
                 chain("sstA", self.sst, d["sst"], d["sst_field_idx"], d["sst_T"], d["sst_rcrit"], d["lat"], (self.sB, nS))
             with torch.cuda.stream(sSb):
                 chain("sstB", self.sst, d["sst"], d["sst_field_idx"], d["sst_T"], d["sst_rcrit"], d["lat"], (0, self.sB))
-        chain("sicB", self.sic, d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"], (0, self.jB))
+        main.wait_stream(sB)
         with torch.cuda.stream(sA):
             chainA_done = torch.cuda.Event()
             chainA_done.record()
