@@ -280,7 +280,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
       res = __dadd_rn(res, __shfl_xor_sync(gmask, res, 2));
       res = __dadd_rn(res, __shfl_xor_sync(gmask, res, 4));
     }
-    for (int t = 0; t < nt; ++t) res = __dadd_rn(res, __shfl_sync(gmask, tv, t, 8));   // tail, left to right
+    res = sie_add_tail8(res, tv, nt, gmask);           // tail, left to right
     nanc += __shfl_xor_sync(gmask, nanc, 1);
     nanc += __shfl_xor_sync(gmask, nanc, 2);
     nanc += __shfl_xor_sync(gmask, nanc, 4);

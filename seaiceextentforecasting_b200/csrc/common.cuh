@@ -56,6 +56,17 @@ template <> __device__ __forceinline__ void sie_fence_regs<16>(double (&v)[16]) 
                     "+d"(v[8]), "+d"(v[9]), "+d"(v[10]), "+d"(v[11]), "+d"(v[12]), "+d"(v[13]), "+d"(v[14]), "+d"(v[15]));
 }
 
+// res + tail[0] + tail[1] + ... (left to right), tail element t held by lane t of the 8-lane group: the <= 7 shuffles are
+// issued back to back, then the adds run as one dependent chain (a runtime loop would pay shuffle latency per step).
+__device__ __forceinline__ double sie_add_tail8(double res, double tv, int nt, unsigned gmask) {
+  double t[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) t[i] = __shfl_sync(gmask, tv, i, 8);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) if (i < nt) res = __dadd_rn(res, t[i]);
+  return res;
+}
+
 // Lane j's part of one leaf: accumulator j over the `ngrp` full groups of 8 (sequential, numpy's order) and tail
 // element j.  The NQ + 1 gathers are unconditional (indices clamped to the last element; the extras are masked
 // out of the sums) so they are issued back to back.  get(i) must be valid for lo <= i < lo + n.
@@ -109,7 +120,7 @@ __device__ __forceinline__ double sie_pw_leaf8(Get get, int lo, int n, int j, un
     r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
     res = r;
   }
-  for (int t = 0; t < ntail; ++t) res = __dadd_rn(res, __shfl_sync(gmask, tv, t, 8));   // tail, left to right
+  res = sie_add_tail8(res, tv, ntail, gmask);        // tail, left to right
   return res;
 }
 
@@ -137,7 +148,7 @@ __device__ __forceinline__ double sie_pw_leaf8_contig_n(const double* q, int ngr
     res = r;
   }
   const double tv = (j < nt) ? t[0] : 0.0;
-  for (int i = 0; i < nt; ++i) res = __dadd_rn(res, __shfl_sync(gmask, tv, i, 8));
+  res = sie_add_tail8(res, tv, nt, gmask);
   return res;
 }
 __device__ __forceinline__ double sie_pw_leaf8_contig(const double* q, int n, int j, unsigned gmask) {
