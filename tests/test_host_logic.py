@@ -185,3 +185,51 @@ def test_retro_csv_layout_matches_reference_script():
     ref_rt = pd.DataFrame(data_rt, index=years, columns=columns2)
     assert df_dt.equals(ref_dt) and df_rt.equals(ref_rt)
     assert list(df_dt.index) == years and list(df_dt.columns) == columns1
+
+
+def _tau_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from seaiceextentforecasting_b200.parallel import shard_tile_rows, tau_from_shards
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)                 # same matrix on every rank
+    N, rc = 700, 0.35
+    Z = rng.standard_normal((N, 30))
+    Z -= Z.mean(1, keepdims=True)
+    Z /= np.linalg.norm(Z, axis=1, keepdims=True)
+    R = np.clip(Z @ Z.T, -1, 1)
+    np.fill_diagonal(R, np.nan)
+    s = c = 0.0
+    for bi in shard_tile_rows(N, rank, world):     # what sie_corr_tau(shard_rank, shard_count) covers: rows of the upper triangle
+        rows = slice(128 * bi, min(N, 128 * bi + 128))
+        blk = R[rows, :]
+        upper = np.triu(np.ones_like(R, dtype=bool), 1)[rows, :]
+        m = upper & (blk >= 0) & (blk > rc)
+        s += 2.0 * blk[m].sum()
+        c += 2 * int(m.sum())
+    tau = tau_from_shards(torch.tensor([s], dtype=torch.float64), torch.tensor([c], dtype=torch.int64))
+    if rank == 0:
+        full = R[(R >= 0) & (R > rc)]
+        q.put(bool(abs(tau.item() - full.mean()) <= 1e-12 * abs(full.mean())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_sharded_tau_allreduce_two_ranks():
+    """the row-sharded correlation build exchanges only (sum, count); two gloo ranks reproduce the
+    unsharded tau of ComplexNetworks.py:41-47."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tau_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+    assert ok

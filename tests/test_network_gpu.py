@@ -149,3 +149,47 @@ def test_corrs_lazy_view(lib_built):
     m = ~np.isnan(o.corrs)
     assert np.max(np.abs(c[m] - o.corrs[m])) <= 1e-9
     assert n.corrs[3, 4, 5] == c[3, 4, 5] or np.isnan(c[3, 4, 5])
+
+
+def test_row_sharded_tau_matches_unsharded_and_numpy(lib_built):
+    """configs[3] / SURVEY.md 8(e): `sie_corr_tau(shard_rank, shard_count)` with R not stored -- the shards' partial
+    (sum, count) add up to the unsharded result, and tau equals the reference formula evaluated with numpy."""
+    import torch
+    from scipy import stats
+    from seaiceextentforecasting_b200.engine import NetworkBatch, h2d, r_crit_ttest
+    from seaiceextentforecasting_b200.parallel import tau_from_shards
+    X, Y, T = 40, 36, 25
+    data, _ = syn.make_field(X, Y, T, 9)
+    n_upper = int((~np.isnan(data).any(axis=2)).sum())
+    eng = NetworkBatch(X, Y, T, 1, latlon=False, n_upper=n_upper, keep_R=False, max_areas=8)
+    f = h2d(data.reshape(1, X * Y, T))
+    jf = torch.zeros(1, dtype=torch.int32, device="cuda")
+    jT = torch.full((1,), T, dtype=torch.int32, device="cuda")
+    rc = h2d(np.array([r_crit_ttest(T, 0.01)]))
+    eng.detrend_zscore(f, jf, jT, True)
+    eng.corr_tau(rc, store_R=False)
+    torch.cuda.synchronize()
+    s_all, c_all, tau_all = eng.tau_sum.item(), eng.tau_cnt.item(), eng.tau.item()
+    for world in (2, 3, 8):
+        ss, cc = 0.0, 0
+        for r in range(world):
+            eng.corr_tau(rc, store_R=False, shard_rank=r, shard_count=world)
+            torch.cuda.synchronize()
+            ss += eng.tau_sum.item()
+            cc += eng.tau_cnt.item()
+        assert cc == c_all
+        assert abs(ss - s_all) <= 1e-12 * abs(s_all)
+    assert abs(tau_from_shards(eng.tau_sum * 0 + s_all, eng.tau_cnt * 0 + c_all).item() - tau_all) <= 1e-15
+    # the reference's formula on the detrended field (ComplexNetworks.py:32-47)
+    from oracle.gp import detrend as odetrend
+    dt, _ = odetrend(data)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ID = np.where(np.abs(np.nanmax(dt, 2)) > 0)
+        R = np.corrcoef(dt[ID])
+        np.fill_diagonal(R, np.nan)
+        df = T - 2
+        P = stats.t.sf(R * np.sqrt(df / (1 - R ** 2)), df)
+        ref = np.mean(R[(R >= 0) & (P < 0.01)])
+    assert abs(tau_all - ref) <= 1e-9 * abs(ref)
