@@ -339,7 +339,7 @@ class RetrospectiveSweep:
     """
 
     def __init__(self, config_names, sic_fields, sie, fmin, fmax, psar, sst_field=None, sst_lat=None,
-                 significance=0.01, max_areas=None, max_pred=384, rank=0, world=1, wave_T=12):
+                 significance=0.01, max_areas=None, max_pred=384, rank=0, world=1, wave_T=(12,)):
         require_cuda()
         self.plan = plan = SweepPlan(config_names, sie, fmin, fmax, significance, rank, world)
         self.cfgs, self.years, self.fmin, self.fmax = plan.cfgs, plan.years, plan.fmin, plan.fmax
@@ -366,24 +366,41 @@ class RetrospectiveSweep:
         self.n_forecasts = plan.P
         self.gp = GpBatch(max(1, self.P), max_pred=max_pred)
         self._side = None
-        # Two waves: (B) long windows, whose domain growth is the slow stage and whose GP problems are small, and
-        # (A) short windows (T <= wave_T), whose networks finish early and whose GP problems (many small areas ->
-        # up to ~160 predictors) are the expensive ones.  Jobs and problems are ordered by descending year, so each
-        # wave is a contiguous range; wave A's GP then overlaps wave B's domain growth.
-        self.wave_T = int(wave_T)
+        # Waves.  Jobs and GP problems are ordered by descending year, so splitting the window lengths at `wave_T` edges
+        # gives contiguous job / problem ranges: wave 0 = the longest windows (slowest domain growth, small GP problems),
+        # the last wave = the shortest windows (networks finish early; their many small areas give the expensive
+        # 100-160-predictor GP problems).  Every wave runs its chain on its own stream and its GP starts as soon as ITS
+        # networks are done, overlapping the domain growth of the longer-window waves.
+        edges = sorted({int(e) for e in (wave_T if isinstance(wave_T, (tuple, list)) else (wave_T,))}, reverse=True)
+        self.wave_T = tuple(edges)
         T = plan.job_T
-        self.jB = int((T > self.wave_T).sum())                       # SIC jobs [0, jB) = wave B, [jB, nJ) = wave A
-        assert (T[:self.jB] > self.wave_T).all() and (T[self.jB:] <= self.wave_T).all()
-        self.sB = int((plan.sst_T > self.wave_T).sum()) if self.use_sst else 0
         prob_T = plan.job_T[plan.prob["job_sic"]] if plan.P else np.zeros(0, dtype=np.int32)
-        self.pB = int((prob_T > self.wave_T).sum())                  # problems [0, pB) only read wave-B... see below
-        ok = plan.P > 0 and (prob_T[:self.pB] > self.wave_T).all() and (prob_T[self.pB:] <= self.wave_T).all()
-        if self.use_sst and plan.P:
-            ps = plan.prob["job_sst"][self.pB:]
-            ok = ok and bool((ps[ps >= 0] >= self.sB).all())         # wave-A problems only read wave-A SST networks
-        self.two_waves = bool(ok and 0 < self.jB < len(plan.jobs) and 0 < self.pB < plan.P and
-                              (not self.use_sst or 0 < self.sB < len(plan.sst_years)))
-        self.gpA = GpBatch(max(1, self.P - self.pB), max_pred=max_pred) if self.two_waves else None
+
+        def cuts(values):                      # descending `values` -> range boundaries [0, c1, c2, ..., len]
+            values = np.asarray(values)
+            return [0] + [int((values > e).sum()) for e in edges] + [len(values)]
+
+        jc, pc = cuts(T), cuts(prob_T)
+        sc = cuts(plan.sst_T) if self.use_sst else [0] * (len(edges) + 2)
+        ok = plan.P > 0 and bool((np.diff(T) <= 0).all()) and bool((np.diff(prob_T) <= 0).all())
+        if self.use_sst:
+            ok = ok and bool((np.diff(plan.sst_T) <= 0).all())
+        self.waves = []                        # (job range, sst range, problem range), longest windows first
+        for w in range(len(edges) + 1):
+            jr, sr, pr = (jc[w], jc[w + 1]), (sc[w], sc[w + 1]), (pc[w], pc[w + 1])
+            if jr[1] > jr[0] or pr[1] > pr[0]:
+                self.waves.append((jr, sr, pr))
+        if ok and self.use_sst and plan.P:     # a wave's problems may only read SST networks of the same or a shorter-window wave
+            for (jr, sr, pr) in self.waves:
+                ps = plan.prob["job_sst"][pr[0]:pr[1]]
+                ok = ok and bool((ps[ps >= 0] >= sr[0]).all())
+        if ok and plan.P:                      # ... and SIC networks of the same or a shorter-window wave (previous-year configs)
+            for (jr, sr, pr) in self.waves:
+                ok = ok and bool((plan.prob["job_sic"][pr[0]:pr[1]] >= jr[0]).all())
+        self.multi_wave = bool(ok and len(self.waves) > 1)
+        self.two_waves = self.multi_wave       # (name kept for callers)
+        self.gp_wave = [GpBatch(max(1, pr[1] - pr[0]), max_pred=max_pred) for (_, _, pr) in self.waves[1:]] \
+            if self.multi_wave else []
         self._streams = None
         # pinned staging buffers so every step pays a real host->device copy
         self._pin = {name: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
@@ -414,7 +431,7 @@ class RetrospectiveSweep:
         (stage name, torch.cuda.Event) pairs recorded after each stage, for per-kernel timing.  `waves`: 1 = one
         batch per grid (stage timing), 2 = short/long-window waves on separate streams (default when possible)."""
         d = self.dev
-        two = self.two_waves if waves is None else (waves == 2 and self.two_waves)
+        two = self.multi_wave if waves is None else (waves != 1 and self.multi_wave)
 
         def mark(name):
             if marks is not None:
@@ -450,40 +467,46 @@ class RetrospectiveSweep:
             self.gp.run(d["prob"], d["y"], self.sic, self.sst)
             mark("gp")
             return
+        nw = len(self.waves)
         if self._streams is None:
-            self._streams = [torch.cuda.Stream(priority=-1) for _ in range(4)]
-        sA, sSb, sSa, sB = self._streams
-        nJ, nS = self.sic.B, (self.sst.B if self.sst is not None else 0)
-        for st in self._streams:
-            st.wait_stream(main)
-        # enqueue order = issue order: the long-window SIC chain (the critical path) goes first; all four chains have the
-        # same priority (measured: 14.3 ms against 15.1 ms with the short-window chain first)
-        with torch.cuda.stream(sB):
-            chain("sicB", self.sic, d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"], (0, self.jB))
-        with torch.cuda.stream(sA):            # wave A: short windows -> the big GP problems
-            chain("sicA", self.sic, d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"], (self.jB, nJ))
-        if self.sst is not None:
-            with torch.cuda.stream(sSa):
-                chain("sstA", self.sst, d["sst"], d["sst_field_idx"], d["sst_T"], d["sst_rcrit"], d["lat"], (self.sB, nS))
-            with torch.cuda.stream(sSb):
-                chain("sstB", self.sst, d["sst"], d["sst_field_idx"], d["sst_T"], d["sst_rcrit"], d["lat"], (0, self.sB))
-        main.wait_stream(sB)
-        with torch.cuda.stream(sA):
-            chainA_done = torch.cuda.Event()
-            chainA_done.record()
-            if self.sst is not None:
-                sA.wait_stream(sSa)
-            mark("gpA.start")
-            self.gpA.run(d["prob"], d["y"], self.sic, self.sst, (self.pB, self.P), out=self.gp.out)
-            mark("gpA")
-        if self.sst is not None:
-            main.wait_stream(sSb)
-            main.wait_stream(sSa)
-        main.wait_event(chainA_done)            # wave-B problems with a previous-year network may read wave-A jobs
-        mark("gpB.start")
-        self.gp.run(d["prob"], d["y"], self.sic, self.sst, (0, self.pB))
-        mark("gpB")
-        main.wait_stream(sA)                    # the step is complete on `main` once wave A's GP has finished too
+            self._streams = [(torch.cuda.Stream(priority=-1), torch.cuda.Stream(priority=-1)) for _ in range(nw)]
+        for (s1, s2) in self._streams:
+            s1.wait_stream(main)
+            s2.wait_stream(main)
+        # enqueue order = issue order: SIC chains from the longest windows (the critical path) to the shortest, then the
+        # SST chains from the shortest to the longest (measured best of the orders tried, tools/timeline.py)
+        seq = [("s", w) for w in range(nw)] + [("t", w) for w in range(nw - 1, -1, -1)]
+        done = [None] * nw
+        for kind, w in seq:
+            jr, sr, pr = self.waves[w]
+            if kind == "s":
+                with torch.cuda.stream(self._streams[w][0]):
+                    if jr[1] > jr[0]:
+                        chain(f"sic{w}", self.sic, d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"], jr)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    done[w] = ev
+            elif self.sst is not None and sr[1] > sr[0]:
+                with torch.cuda.stream(self._streams[w][1]):
+                    chain(f"sst{w}", self.sst, d["sst"], d["sst_field_idx"], d["sst_T"], d["sst_rcrit"], d["lat"], sr)
+        # GP of wave w: needs its own networks and those of the shorter-window waves (previous-year configurations)
+        for w in range(nw - 1, -1, -1):
+            jr, sr, pr = self.waves[w]
+            if pr[1] <= pr[0]:
+                continue
+            st = self._streams[w][0]
+            with torch.cuda.stream(st):
+                for v in range(w, nw):
+                    st.wait_event(done[v])
+                    if self.sst is not None:
+                        st.wait_stream(self._streams[v][1])
+                mark(f"gp{w}.start")
+                gp = self.gp if w == 0 else self.gp_wave[w - 1]
+                gp.run(d["prob"], d["y"], self.sic, self.sst, pr, out=self.gp.out)
+                mark(f"gp{w}")
+        for (s1, s2) in self._streams:          # the step is complete on `main` once every wave has finished
+            main.wait_stream(s1)
+            main.wait_stream(s2)
 
     def hyper_grid(self, ells=None, sigs=None):
         """BASELINE.json configs[4] on this member: every GP problem of the sweep (year x init x region) evaluated on
@@ -506,8 +529,12 @@ class RetrospectiveSweep:
     def kernel_launches(self):
         """Kernels of libsie_b200 enqueued by one compute(): 12 per network batch (K1: 3, K2: 4, K3-K5: 2, K6: 3), per
         wave, + 2 per GP batch."""
-        w = 2 if self.two_waves else 1
-        return w * (12 * (2 if self.use_sst else 1) + 2)
+        if not self.multi_wave:
+            return 12 * (2 if self.use_sst else 1) + 2
+        n = 0
+        for (jr, sr, pr) in self.waves:
+            n += 12 * (jr[1] > jr[0]) + 12 * (self.use_sst and sr[1] > sr[0]) + 2 * (pr[1] > pr[0])
+        return int(n)
 
     def download(self):
         """Device -> host read of the GP results (synchronises)."""

@@ -4,7 +4,7 @@ import numpy as np, torch
 import bench
 from seaiceextentforecasting_b200.config import NORTH_INITS
 from seaiceextentforecasting_b200.forecast import RetrospectiveSweep
-wave_T = int(sys.argv[1]) if len(sys.argv) > 1 else 18
+wave_T = tuple(int(x) for x in sys.argv[1].split(',')) if len(sys.argv) > 1 else (12, 24)
 w = bench.make_workload(0)
 sw = RetrospectiveSweep(NORTH_INITS, w['sic'], w['sie'], bench.FMIN, bench.FMAX, w['psar'], w['sst'], w['lat'], wave_T=wave_T)
 sw.upload()
@@ -14,5 +14,5 @@ for waves in (2, 1):
     e0 = torch.cuda.Event(enable_timing=True); e0.record()
     marks = []; sw.compute(marks, waves=waves)
     e1 = torch.cuda.Event(enable_timing=True); e1.record(); torch.cuda.synchronize()
-    print("waves", waves, "wave_T", wave_T, "total ms", round(e0.elapsed_time(e1), 2), "jB", sw.jB, "pB", sw.pB)
+    print("waves", waves, "wave_T", wave_T, "total ms", round(e0.elapsed_time(e1), 2), "ranges", sw.waves)
     for name, ev in marks: print("   %-22s %7.2f" % (name, e0.elapsed_time(ev)))
