@@ -108,7 +108,8 @@ int sie_corr_stencil(const double* R, const int32_t* node_cell, const int32_t* c
  *            each), 1: SM cycles in step 1, 2: SM cycles in step 2, 3: (growth steps << 32) | merge rounds,
  *            4..14: SM cycles per phase (step 1: seed search, evaluate+argmax, frontier update, gathers;
  *            step 2: select/materialise, neighbour discovery, neighbour lists, row means, statistic,
- *            merge/finalise; 14 unused), 15: growth steps that took the re-summing path}
+ *            merge/finalise; 14 unused), 15: growth steps that took the re-summing path}; the per-phase entries
+ *            4..14 and 16..25 are only filled by a build with -DSIE_AREA_PHASE_TIMERS (they cost ~6 % of the kernel)
  */
 int sie_area_level(const double* R, const double* stencil, const int32_t* node_cell,
                    const int32_t* cell_node, const int32_t* n_nodes, const double* tau,

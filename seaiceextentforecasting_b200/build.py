@@ -12,7 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsie_b200.so")
 SOURCES = ["abi.cu", "detrend.cu", "corr.cu", "area.cu", "links.cu", "gp.cu", "ingest.cu"]
-NVCC_FLAGS = (["-DSIE_AREA_DEBUG_ROUNDS"] if os.environ.get("SIE_DEBUG") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+# SIE_AREA_TIMERS=1: per-phase clock64 counters of k_area_level (work[4..]); they cost ~6 % of the kernel, so the
+# product build leaves them out (tools/prof_sweep.py and tools/prof_one.py need a build with them)
+NVCC_FLAGS = (["-DSIE_AREA_PHASE_TIMERS"] if os.environ.get("SIE_AREA_TIMERS") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 
 

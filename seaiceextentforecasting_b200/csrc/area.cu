@@ -186,6 +186,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   __shared__ unsigned long long sh_work;
   __shared__ unsigned long long ph[16];   // per-phase SM cycles (thread 0's view), reported through work[4..15]
   long long tick_last = 0;
+#ifdef SIE_AREA_PHASE_TIMERS
 #define TICK(i)                                                        \
   do {                                                                 \
     if (tid == 0) {                                                    \
@@ -194,15 +195,22 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
       tick_last = t__;                                                 \
     }                                                                  \
   } while (0)
+#else
+#define TICK(i) do { } while (0)
+#endif
   unsigned long long wk = 0;   // correlations consumed (algorithmic gathers)
   unsigned long long bph[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // bookkeeping-warp phase cycles (its lane 0), work[16..23]
   long long btick = 0;
+#ifdef SIE_AREA_PHASE_TIMERS
 #define BTICK(i)                                                       \
   do {                                                                 \
     const long long t__ = clock64();                                   \
     bph[i] += (unsigned long long)(t__ - btick);                       \
     btick = t__;                                                       \
   } while (0)
+#else
+#define BTICK(i) do { } while (0)
+#endif
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -1,4 +1,5 @@
-"""Phase cycles of k_area_level for ONE 57x57x42 network (B=1: no other CTA competes for the memory system)."""
+"""(needs a library built with per-phase timers: SIE_AREA_TIMERS=1 python seaiceextentforecasting_b200/build.py --force)
+Phase cycles of k_area_level for ONE 57x57x42 network (B=1: no other CTA competes for the memory system)."""
 import sys, os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench

@@ -1,3 +1,4 @@
+# needs a library built with per-phase timers: SIE_AREA_TIMERS=1 python seaiceextentforecasting_b200/build.py --force
 import sys, json
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
