@@ -639,10 +639,9 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         }
       }
       sh_x[0] = top; sh_x[1] = ok; sh_x[2] = stop;
-      unsigned long long cons = 0;     // correlations the reference consumes this round: n(n-1)/2 per neighbour
-      for (int q = 0; q < nn; ++q) { const unsigned long long n = (unsigned long long)(nb + S.size[S.nlist[q]]); cons += n * (n - 1) / 2; }
-      wk += cons;
     }
+    // correlations the reference consumes this round: n(n-1)/2 per neighbour (work counter only)
+    for (int q = tid; q < nn; q += NT) { const unsigned long long n = (unsigned long long)(nb + S.size[S.nlist[q]]); wk += n * (n - 1) / 2; }
     __syncthreads();
     xtop = sh_x[0];
     self_top = sh_x[2];
@@ -680,6 +679,8 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
       }
       __syncthreads();
       for (int q = q0; q < q1; ++q) {
+        // dense rounds only need a neighbour's node list while its cross block / self means are being filled
+        if (dense && sh_goff[q - q0 + 1] == sh_goff[q - q0] && sh_soff[q - q0 + 1] == sh_soff[q - q0]) continue;
         int off = sh_koff[q - q0];
         for (int s = S.nlist[q]; s >= 0; s = S.seg_next[s]) {
           const int st = S.a_start[s], ln = S.a_len[s];

@@ -27,3 +27,10 @@ for i in list(order[:12])+list(order[-3:]):
     print(i,sw.plan.prob_meta[i],sw.plan.prob[i]['n'],raw[i]['n_pred'],raw[i]['expm_m'],raw[i]['expm_s'],raw[i]['info'],round(raw[i]['cycles_total']/1e6,3),round(raw[i]['cycles_expm']/1e6,3))
 print('gp sum total Mcyc',raw['cycles_total'].sum()/1e6,'expm',raw['cycles_expm'].sum()/1e6, 'bad',[(i,sw.plan.prob_meta[i],raw[i]['info'],raw[i]['n_pred']) for i in np.nonzero(raw['info'])[0]])
 print('s hist',np.bincount(raw['expm_s']), 'npred max',raw['n_pred'].max(), 'mean', raw['n_pred'].mean())
+# GP problems of the long-window wave (T > 12): what the tail of the step looks like
+pm = np.array(sw.plan.prob_meta)
+Tp = sw.plan.job_T[sw.plan.prob["job_sic"]]
+for lo, hi in ((13, 20), (21, 30), (31, 42)):
+    sel = np.nonzero((Tp >= lo) & (Tp <= hi))[0]
+    c = raw['cycles_total'][sel] / 1e6
+    print(f"gp T {lo}-{hi}: {len(sel)} problems, sum {c.sum():.1f} Mcyc, max {c.max():.2f}, Np max {raw['n_pred'][sel].max()}, mean {raw['n_pred'][sel].mean():.1f}, s max {raw['expm_s'][sel].max()}")
