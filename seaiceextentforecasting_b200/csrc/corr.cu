@@ -7,9 +7,11 @@
 // kind, and ptxas splits the larger sm_90 f64 shapes into 8x8x4 on sm_100a).  A 128-row panel of Z is one
 // contiguous 128*Tp*8-byte run, so operands are staged with 1-D bulk async copies (cp.async.bulk -> SASS
 // UBLKCP, the TMA engine) completing on an mbarrier; Tp = 4 (mod 8) makes the fragment loads
-// bank-conflict free without swizzling.  Persistent CTAs (one per SM) walk the upper-triangular
-// 128x128 tile list with a 2-stage full/empty pipeline; only bi <= bj tiles are computed and results are
-// mirrored, so R is bitwise symmetric like numpy's syrk-based corrcoef.
+// bank-conflict free without swizzling.  Persistent 256-thread CTAs (two per SM, so one CTA's stores overlap
+// the other's MMAs) walk a precomputed table of 128x64 tiles on or right of the diagonal blocks; only those
+// tiles are computed and results are mirrored, so R is bitwise symmetric like numpy's syrk-based corrcoef
+// (SURVEY.md H1).  Off-diagonal tiles are staged in shared memory (over the operand panels) and written as
+// whole rows: 512-byte runs for the tile, 1-KB runs for its transpose.
 // Algorithmic work: N(N+1)T flop per network (upper triangle), 8 N^2 bytes if R is stored.
 #include "common.cuh"
 

@@ -59,7 +59,14 @@ def compare_networks(n, o, dt):
     np.testing.assert_allclose(n.strengthmap[ok], o.strengthmap[ok], rtol=1e-9)
 
 
-@pytest.mark.parametrize("X,Y,T,latlon,seed", CASES)
+MORE_CASES = [  # wider seeded sweep of shapes / window lengths (T = 7 gives many two-cell areas, long T few big ones)
+    (30, 28, 7, False, 101), (30, 28, 8, False, 102), (41, 37, 12, False, 103), (41, 37, 42, False, 104),
+    (18, 60, 7, True, 105), (18, 60, 25, True, 106), (26, 90, 9, True, 107), (57, 57, 7, False, 108),
+    (57, 57, 19, False, 109), (48, 52, 33, False, 110), (22, 44, 42, True, 111), (64, 40, 15, False, 112),
+]
+
+
+@pytest.mark.parametrize("X,Y,T,latlon,seed", CASES + MORE_CASES)
 def test_network_matches_oracle(lib_built, X, Y, T, latlon, seed):
     from oracle.gp import detrend as odetrend
     from seaiceextentforecasting_b200.forecast import detrend
