@@ -90,8 +90,10 @@ __global__ void k_tile_prefix(const int32_t* __restrict__ n_nodes, int B, int ld
   }
 }
 
-// item -> (job, 128-row block, 64-column block), written once so the tile loop decodes with one 16-byte load
-__global__ void k_tile_table(const int32_t* __restrict__ n_nodes, int ldn, int rank, int count,
+// item -> two int4: (job, 128-row block, 64-column block, N) and (k-steps, 0, int64 image of the threshold), written
+// once so the tile loops decode with one 32-byte load and no dependent per-job loads
+__global__ void k_tile_table(const int32_t* __restrict__ n_nodes, const int32_t* __restrict__ job_T,
+                             const double* __restrict__ r_crit, int ldn, int rank, int count,
                              const long long* __restrict__ prefix, int4* __restrict__ table) {
   const int b = blockIdx.x, q = blockIdx.y;
   const int N = min(n_nodes[b], ldn);
@@ -99,7 +101,13 @@ __global__ void k_tile_table(const int32_t* __restrict__ n_nodes, int ldn, int r
   if (q >= shard_rows(nb, rank, count)) return;
   const int bi = rank + q * count;
   const long long base = prefix[b] + shard_tiles_before(q, nc, rank, count);
-  for (int t = threadIdx.x; t < nc - 2 * bi; t += blockDim.x) table[base + t] = make_int4(b, bi, 2 * bi + t, 0);
+  const double rc = r_crit[b];
+  const long long rcb = rc < 0.0 ? -1LL : __double_as_longlong(rc);
+  const int4 meta = make_int4((job_T[b] + 3) >> 2, 0, (int)(unsigned)(rcb & 0xffffffffLL), (int)(rcb >> 32));
+  for (int t = threadIdx.x; t < nc - 2 * bi; t += blockDim.x) {
+    table[2 * (base + t)] = make_int4(b, bi, 2 * bi + t, N);
+    table[2 * (base + t) + 1] = meta;
+  }
 }
 
 __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM)
@@ -128,7 +136,7 @@ k_corr_tiles(const double* __restrict__ z, const int32_t* __restrict__ n_nodes,
   const uint32_t b_bytes = (uint32_t)((size_t)TILE_N * Tp * sizeof(double));
 
   auto decode = [&](long long item, int& b, int& bi, int& bj) {
-    const int4 e = table[item];
+    const int4 e = table[2 * item];
     b = e.x; bi = e.y; bj = e.z;
   };
 
@@ -327,21 +335,325 @@ k_corr_tiles(const double* __restrict__ z, const int32_t* __restrict__ n_nodes,
   }
 }
 
-// one warp per job: fixed-order reduction of the tile partials -> tau_sum, tau_cnt, tau
-__global__ void k_tau_finalize(const double* __restrict__ tile_part, const long long* __restrict__ prefix,
-                               int B, double* __restrict__ tau_sum, int64_t* __restrict__ tau_cnt,
-                               double* __restrict__ tau) {
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (b >= B) return;
+// -------------------------------------------------------------------------------------------------
+// k_corr_rows: the row-resident, warp-specialised form of the same contraction (used whenever its shared
+// memory fits; k_corr_tiles above remains the fallback for very long windows).
+//   * one persistent CTA per SM walks a CONTIGUOUS run of the tile table, so the 128-row A panel of a tile row
+//     stays in shared memory for the whole row and only the 64-row B panels stream (22.5 KB per tile instead of
+//     67.6 KB out of L2);
+//   * warp 16 is the producer: lane 0 keeps an S-stage ring of B panels full with bulk async copies (full/empty
+//     mbarriers); warps 0-15 (4 x 4, a 32 x 16 sub-tile = 4 x 2 DMMA blocks each) compute.  Everything a tile needs
+//     (job, block indices, N, k-steps, threshold image) sits in one 32-byte table entry that is prefetched a tile
+//     ahead, so no dependent global load precedes the MMAs;
+//   * STORE: the finished tile is staged in shared memory twice - as is (rows padded to 576 B) and transposed
+//     (rows padded to 1040 B; both paddings make the fragment-layout writes bank-conflict free) - and written
+//     with whole-row 16-byte stores: 512-byte runs for the tile, 1-KB runs for its mirror (tools/micro/wpat.cu:
+//     plain stores of such runs reach > 6 TB/s, one bulk async store per run only 2.3-4.6 TB/s).  The stores are
+//     fire-and-forget and drain while the CTA is already in the MMAs of the next tile - the panels are NOT
+//     overlaid by the staging buffers.  Whole tiles are written, so the zero padding of R (rows/columns N..ldn of
+//     the last blocks) is written too; the diagonal blocks are symmetrised in the staging buffer (only the strict
+//     upper triangle is taken from the accumulators) so R stays bitwise symmetric;
+//   * !STORE (25 km row shards): no staging, deeper ring, no CTA-wide barrier at all;
+//   * thresholds are integer compares on the bit patterns, which leaves only the predicated DADD on the FP64 pipe.
+// Per-tile tau partials are written per warp ([tile][16][2]), folded per tile by k_tau_tiles and reduced per
+// job in a fixed order by k_tau_finalize.
+// -------------------------------------------------------------------------------------------------
+constexpr int RW_CWARPS = 16;                    // consumer warps (4 x 4)
+constexpr int RW_SWARPS = 15;                    // store warps (STORE only): one warp sustains only ~3.6 GB/s of stores
+                                                 // (tools/micro/wpat.cu), HBM's share per SM needs >= 12 of them
+constexpr int RW_MAXS = 6;                       // deepest B ring
+constexpr int RW_D_LD = TILE_N + 8;              // 72 doubles = 576 B per staged row
+constexpr int RW_T_LD = TILE + 2;                // 130 doubles = 1040 B per staged transposed row
+template <bool STORE> constexpr int rw_threads() { return (RW_CWARPS + 1 + (STORE ? RW_SWARPS : 0)) * 32; }
+
+// clip to [-1, 1] (np.clip keeps NaN): one integer compare on the high word in the common |v| < 1 case
+__device__ __forceinline__ double clip_unit(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu;
+  if (hi >= 0x3ff00000u) {
+    if (v > 1.0) v = 1.0;
+    else if (v < -1.0) v = -1.0;
+  }
+  return v;
+}
+
+template <bool STORE>
+__global__ void __launch_bounds__(rw_threads<STORE>(), 1)
+k_corr_rows(const double* __restrict__ z, const long long* __restrict__ prefix, const int4* __restrict__ table,
+            int B, int ldn, int Tp, int S, double* __restrict__ R, double* __restrict__ parts) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sA = reinterpret_cast<double*>(smem_raw);               // [128][Tp]
+  double* sB = sA + (size_t)TILE * Tp;                            // [S][64][Tp]
+  double* sD = sB + (size_t)S * TILE_N * Tp;                      // [128][RW_D_LD]   (STORE)
+  double* sT = sD + (size_t)TILE * RW_D_LD;                       // [64][RW_T_LD]    (STORE)
+  __shared__ uint64_t full_bar[RW_MAXS], empty_bar[RW_MAXS];
+  __shared__ uint64_t d_full, d_free, t_full, t_free;             // staging handshakes consumers <-> store warps
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long total = prefix[B];
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long lo = (long long)blockIdx.x * per;
+  const long long hi = lo + per < total ? lo + per : total;
+  const int n = (int)(hi - lo);
+  if (n <= 0) return;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], RW_CWARPS); }
+    mbar_init(&d_full, RW_CWARPS); mbar_init(&t_full, RW_CWARPS);
+    mbar_init(&d_free, RW_SWARPS); mbar_init(&t_free, RW_SWARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t a_bytes = (uint32_t)((size_t)TILE * Tp * sizeof(double));
+  const uint32_t b_bytes = (uint32_t)((size_t)TILE_N * Tp * sizeof(double));
+
+  if (warp >= RW_CWARPS) {
+  // 1024 threads start with 64 registers each: the 4 consumer warpgroups take 80, the other 4 give back down to 48
+  if (STORE) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+  if (warp == RW_CWARPS) {
+    // ---------------- producer warp
+    if (lane != 0) return;
+    int cur_b = -1, cur_bi = -1;
+    int4 e = table[2 * lo];
+    for (int nl = 0; nl < n; ++nl) {
+      const int4 en = table[2 * (lo + (nl + 1 < n ? nl + 1 : nl))];   // next entry in flight during the waits
+      const int s = nl % S, f = nl / S;
+      if (f > 0) mbar_wait(&empty_bar[s], (f - 1) & 1);               // the ring slot is free
+      const bool new_row = (e.x != cur_b || e.y != cur_bi);
+      if (new_row) {
+        // every consumer must be done with the old A panel: wait for the tiles still in the ring
+        for (int j = (nl - S + 1 > 0 ? nl - S + 1 : 0); j < nl; ++j) mbar_wait(&empty_bar[j % S], (j / S) & 1);
+        cur_b = e.x; cur_bi = e.y;
+      }
+      mbar_expect_tx(&full_bar[s], b_bytes + (new_row ? a_bytes : 0u));
+      if (new_row) bulk_g2s(sA, z + ((size_t)e.x * ldn + (size_t)e.y * TILE) * Tp, a_bytes, &full_bar[s]);
+      bulk_g2s(sB + (size_t)s * TILE_N * Tp, z + ((size_t)e.x * ldn + (size_t)e.z * TILE_N) * Tp, b_bytes, &full_bar[s]);
+      e = en;
+    }
+    return;
+  }
+
+  if (STORE && warp > RW_CWARPS) {
+    // ---------------- store warps: staged tile -> R with whole-row 16-byte stores, while the consumers compute
+    const int sw = warp - RW_CWARPS - 1;
+    int4 e = table[2 * lo];
+    for (int k = 0; k < n; ++k) {
+      const int4 en = table[2 * (lo + (k + 1 < n ? k + 1 : k))];
+      const int row0 = e.y * TILE, col0 = e.z * TILE_N, dk = e.z - 2 * e.y;
+      double* Rb = R + (size_t)e.x * ldn * ldn;
+      // the tile: staged row r -> 512 B of R row row0+r (rows 64.. of the first diagonal tile are mirrors: skipped)
+      const int nrow = dk == 0 ? 64 : TILE;
+      mbar_wait(&d_full, k & 1);
+      for (int r0 = sw; r0 < nrow; r0 += 4 * RW_SWARPS) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u * RW_SWARPS;
+          if (r < nrow) v[u] = *reinterpret_cast<const double2*>(sD + (size_t)r * RW_D_LD + 2 * lane);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u * RW_SWARPS;
+          if (r < nrow) *reinterpret_cast<double2*>(Rb + (size_t)(row0 + r) * ldn + col0 + 2 * lane) = v[u];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d_free);
+      // its mirror: staged transposed row c -> 1 KB (512 B for the second diagonal tile) of R row col0+c
+      mbar_wait(&t_full, k & 1);
+      if (dk != 0) {
+        const int nh = dk == 1 ? 1 : 2;
+        for (int c0 = sw; c0 < TILE_N; c0 += 2 * RW_SWARPS) {
+          double2 v[2][2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int c = c0 + u * RW_SWARPS;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              if (c < TILE_N) v[u][h] = *reinterpret_cast<const double2*>(sT + (size_t)c * RW_T_LD + 64 * h + 2 * lane);
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int c = c0 + u * RW_SWARPS;
+            double* dst = Rb + (size_t)(col0 + c) * ldn + row0 + 2 * lane;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              if (c < TILE_N && h < nh) *reinterpret_cast<double2*>(dst + 64 * h) = v[u][h];
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_free);
+      e = en;
+    }
+    return;
+  }
+  return;
+  }
+
+  // ---------------- consumers
+  if (STORE) asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
+  const int wr = warp >> 2, wc = warp & 3;
+  const double* pa = sA + (size_t)(wr * 32 + (lane >> 2)) * Tp + (lane & 3);
+  int4 e0 = table[2 * lo], e1 = table[2 * lo + 1];
+  for (int k = 0; k < n; ++k) {
+    const long long item = lo + k;
+    const int bi = e0.y, bj = e0.z, N = e0.w, ksteps = e1.x;
+    // `R >= 0 && R > rc` (ComplexNetworks.py:44-45) on the bit patterns: for rc >= 0 a double is > rc exactly when
+    // its int64 image is (negative doubles have negative images); rc < 0 leaves `R >= 0` = non-negative image
+    const long long rcb = (long long)(((unsigned long long)(unsigned)e1.w << 32) | (unsigned)e1.z);
+    {
+      const long long nx = item + 1 < hi ? item + 1 : item;       // next tile's entry: in flight during the MMAs
+      e0 = table[2 * nx];
+      e1 = table[2 * nx + 1];
+    }
+    const int s = k % S;
+    const double* pb = sB + (size_t)s * TILE_N * Tp + (size_t)(wc * 16 + (lane >> 2)) * Tp + (lane & 3);
+
+    mbar_wait(&full_bar[s], (k / S) & 1);
+    double acc[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 4
+    for (int ks = 0; ks < ksteps; ++ks) {
+      double af[4], bf[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = pa[(size_t)i * 8 * Tp + ks * 4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bf[j] = pb[(size_t)j * 8 * Tp + ks * 4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);                     // this warp no longer reads the panels
+
+    const int row0 = bi * TILE, col0 = bj * TILE_N;
+    const int dk = bj - 2 * bi;                                    // 0 / 1: the two tiles of the diagonal block
+    const bool interior = dk >= 2 && row0 + TILE <= N && col0 + TILE_N <= N;
+    // the 64 x 64 square on the diagonal sits in rows dsq.. of the tile (dk = 0: rows 0-63, dk = 1: rows 64-127)
+    const int dsq = dk == 0 ? 0 : (dk == 1 ? 64 : -1);
+    double lsum = 0.0;
+    int lcnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { acc[i][j][0] = clip_unit(acc[i][j][0]); acc[i][j][1] = clip_unit(acc[i][j][1]); }
+    // ---- pass 1: tau partial + the tile as is
+    if (STORE && k > 0) mbar_wait(&d_free, (k - 1) & 1);           // tile k-1 has left sD
+    if (interior) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int li = wr * 32 + i * 8 + (lane >> 2);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int lj = wc * 16 + j * 8 + 2 * (lane & 3);
+          const double v0 = acc[i][j][0], v1 = acc[i][j][1];
+          const bool t0 = __double_as_longlong(v0) > rcb, t1 = __double_as_longlong(v1) > rcb;
+          lsum += t0 ? v0 : 0.0;                                   // adding +0.0 leaves a non-negative sum unchanged
+          lsum += t1 ? v1 : 0.0;
+          lcnt += (int)t0 + (int)t1;
+          if (STORE) *reinterpret_cast<double2*>(sD + li * RW_D_LD + lj) = make_double2(v0, v1);
+        }
+      }
+    } else {
+      // tiles of the diagonal block and of the ragged edge
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int li = wr * 32 + i * 8 + (lane >> 2);
+        const int gi = row0 + li;
+        const bool in_sq = dsq >= 0 && li >= dsq && li < dsq + 64;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int lj = wc * 16 + j * 8 + 2 * (lane & 3);
+          const int gj = col0 + lj;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double v = acc[i][j][h];
+            const bool up = gi < N && gj + h < N && (dk >= 2 || gj + h > gi);   // strictly above the diagonal
+            const bool t = up && __double_as_longlong(v) > rcb;
+            lsum += t ? v : 0.0;
+            lcnt += (int)t;
+            if (STORE) {
+              if (in_sq) {
+                const int a = li - dsq, c = lj + h;               // position inside the diagonal square
+                if (c > a) { sD[li * RW_D_LD + c] = v; sD[(dsq + c) * RW_D_LD + a] = v; }
+                else if (c == a) sD[li * RW_D_LD + c] = sie_nan();
+              } else if (dk != 0) {
+                sD[li * RW_D_LD + lj + h] = v;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (STORE) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d_full);
+      // ---- pass 2: the transposed tile (nothing for the first diagonal tile and for the diagonal square)
+      if (k > 0) mbar_wait(&t_free, (k - 1) & 1);                  // tile k-1 has left sT
+      if (dk != 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int li = wr * 32 + i * 8 + (lane >> 2);
+          if (dk == 1 && li >= 64) continue;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int lj = wc * 16 + j * 8 + 2 * (lane & 3);
+            sT[lj * RW_T_LD + li] = acc[i][j][0];
+            sT[(lj + 1) * RW_T_LD + li] = acc[i][j][1];
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_full);
+    }
+    double lc = (double)lcnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+      lc += __shfl_xor_sync(0xffffffffu, lc, o);
+    }
+    if (lane == 0) *reinterpret_cast<double2*>(parts + (item * RW_CWARPS + warp) * 2) = make_double2(lsum, lc);
+  }
+}
+
+// one thread per tile: the 16 warp partials of k_corr_rows in warp order, doubled (both triangles) -> one pair per tile
+__global__ void k_tau_tiles(const double* __restrict__ parts, const long long* __restrict__ prefix, int B,
+                            double* __restrict__ tile_pair) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= prefix[B]) return;
+  const double2* p = reinterpret_cast<const double2*>(parts) + i * RW_CWARPS;
+  double2 v[RW_CWARPS];
+#pragma unroll
+  for (int w = 0; w < RW_CWARPS; ++w) v[w] = p[w];
+  double ts = 0.0, tc = 0.0;
+#pragma unroll
+  for (int w = 0; w < RW_CWARPS; ++w) { ts += v[w].x; tc += v[w].y; }
+  reinterpret_cast<double2*>(tile_pair)[i] = make_double2(2.0 * ts, 2.0 * tc);
+}
+
+// one 256-thread block per job: fixed-order reduction of the per-tile pairs -> tau_sum, tau_cnt, tau
+// (thread t adds tiles t, t+256, ... in order; then a fixed shuffle tree and a fixed warp order)
+__global__ void __launch_bounds__(256)
+k_tau_finalize(const double* __restrict__ tile_pair, const long long* __restrict__ prefix, double* __restrict__ tau_sum,
+               int64_t* __restrict__ tau_cnt, double* __restrict__ tau) {
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ double rs[8], rc[8];
+  const double2* tp = reinterpret_cast<const double2*>(tile_pair);
   double s = 0.0, c = 0.0;
-  for (long long i = prefix[b] + lane; i < prefix[b + 1]; i += 32) { s += tile_part[2 * i]; c += tile_part[2 * i + 1]; }
+  for (long long i = prefix[b] + threadIdx.x; i < prefix[b + 1]; i += 256) { const double2 v = tp[i]; s += v.x; c += v.y; }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
     c += __shfl_xor_sync(0xffffffffu, c, o);
   }
-  if (lane == 0) {
+  if (lane == 0) { rs[warp] = s; rc[warp] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = 0.0; c = 0.0;
+    for (int w = 0; w < 8; ++w) { s += rs[w]; c += rc[w]; }
     tau_sum[b] = s;
     tau_cnt[b] = (int64_t)c;
     tau[b] = s / c;     // 0/0 -> NaN like np.mean([])
@@ -380,7 +692,8 @@ __global__ void k_stencil(const double* __restrict__ R, const int32_t* __restric
 extern "C" size_t sie_corr_tau_scratch_bytes(int B, int ldn) {
   long long nb = (ldn + TILE - 1) / TILE;
   long long tiles = (long long)B * nb * (nb + 1);      // 128 x 64 tiles on or right of the diagonal blocks
-  return (size_t)(tiles * (2 * sizeof(double) + sizeof(int4)) + (size_t)(B + 1) * sizeof(long long) + 512);
+  return (size_t)(tiles * (2 * RW_CWARPS * sizeof(double) + 2 * sizeof(int4) + 2 * sizeof(double)) +
+                  (size_t)(B + 1) * sizeof(long long) + 1024);
 }
 
 extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32_t* job_T,
@@ -400,29 +713,60 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if ((int)smem + 1024 > max_optin) {
-    sie_set_error("sie_corr_tau: Tp=%d needs %zu B of shared memory (> %d)", Tp, smem, max_optin);
-    return SIE_ERR_UNSUPPORTED;
-  }
-  // scratch layout: [prefix (B+1) int64][pad to 256][tile partials][pad to 256][item table]
+  // scratch layout: [prefix (B+1) int64][pad to 256][warp partials 16 pairs/tile][pad][item table 32 B/tile][pad][tile pairs]
   long long* prefix = reinterpret_cast<long long*>(tile_part);
-  size_t off = (((size_t)(B + 1) * sizeof(long long)) + 255) / 256 * 256;
-  double* parts = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(tile_part) + off);
+  unsigned char* base = reinterpret_cast<unsigned char*>(tile_part);
   long long nb = ldn / TILE;
   long long max_items = (long long)B * nb * (nb + 1);
-  size_t off2 = (off + (size_t)max_items * 2 * sizeof(double) + 255) / 256 * 256;
-  int4* table = reinterpret_cast<int4*>(reinterpret_cast<unsigned char*>(tile_part) + off2);
-  SIE_CHECK_ARG(off2 + (size_t)max_items * sizeof(int4) <= tile_part_bytes, "tile_part scratch too small");
+  size_t off = (((size_t)(B + 1) * sizeof(long long)) + 255) / 256 * 256;
+  double* parts = reinterpret_cast<double*>(base + off);
+  size_t off2 = (off + (size_t)max_items * 2 * RW_CWARPS * sizeof(double) + 255) / 256 * 256;
+  int4* table = reinterpret_cast<int4*>(base + off2);
+  size_t off3 = (off2 + (size_t)max_items * 2 * sizeof(int4) + 255) / 256 * 256;
+  double* tile_pair = reinterpret_cast<double*>(base + off3);
+  SIE_CHECK_ARG(off3 + (size_t)max_items * 2 * sizeof(double) <= tile_part_bytes, "tile_part scratch too small");
   k_tile_prefix<<<1, 32, 0, st>>>(n_nodes, B, ldn, shard_rank, shard_count, prefix);
   SIE_CHECK_LAUNCH();
-  k_tile_table<<<dim3((unsigned)B, (unsigned)nb), 128, 0, st>>>(n_nodes, ldn, shard_rank, shard_count, prefix, table);
+  k_tile_table<<<dim3((unsigned)B, (unsigned)nb), 128, 0, st>>>(n_nodes, job_T, r_crit, ldn, shard_rank, shard_count, prefix,
+                                                              table);
   SIE_CHECK_LAUNCH();
-  cudaFuncSetAttribute(k_corr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const long long slots = (long long)CTAS_PER_SM * sms;
-  int grid = (int)(max_items < slots ? max_items : slots);
-  k_corr_tiles<<<grid, NTHREADS, smem, st>>>(z, n_nodes, job_T, r_crit, prefix, table, B, ldn, Tp, R, parts);
-  SIE_CHECK_LAUNCH();
-  k_tau_finalize<<<(B + 3) / 4, 128, 0, st>>>(parts, prefix, B, tau_sum, tau_cnt, tau);
+  // row-resident kernel when its shared memory fits (always for the 1979-2020 windows, Tp <= 44), else the tile kernel
+  const size_t rw_fixed = (size_t)TILE * Tp * sizeof(double) +
+                          (R ? ((size_t)TILE * RW_D_LD + (size_t)TILE_N * RW_T_LD) * sizeof(double) : 0);
+  const size_t rw_stage = (size_t)TILE_N * Tp * sizeof(double);
+  int S = (size_t)max_optin < rw_fixed + 256 ? 0 : (int)(((size_t)max_optin - 256 - rw_fixed) / rw_stage);
+  if (S > RW_MAXS) S = RW_MAXS;
+  // default: rows kernel for the tau-only pass (25.2 vs 22.6 TFLOP/s at 25 km), tile kernel when R is stored (2.14 vs
+  // 2.29 ms on the 144-network sweep: the staged tile's extra trip through the LSU pipe costs what the resident A
+  // panel saves).  SIE_CORR_KERNEL=tiles|rows overrides (A/B timing, parity tests of both paths).
+  const char* force = getenv("SIE_CORR_KERNEL");
+  const bool want_rows = force ? force[0] == 'r' : (R == nullptr);
+  const bool use_rows = S >= 2 && want_rows;
+  if (use_rows) {
+    const size_t rsmem = rw_fixed + (size_t)S * rw_stage;
+    const int grid = (int)(max_items < sms ? max_items : sms);
+    if (R) {
+      cudaFuncSetAttribute(k_corr_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      k_corr_rows<true><<<grid, rw_threads<true>(), rsmem, st>>>(z, prefix, table, B, ldn, Tp, S, R, parts);
+    } else {
+      cudaFuncSetAttribute(k_corr_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      k_corr_rows<false><<<grid, rw_threads<false>(), rsmem, st>>>(z, prefix, table, B, ldn, Tp, S, R, parts);
+    }
+    SIE_CHECK_LAUNCH();
+    k_tau_tiles<<<(unsigned)((max_items + 255) / 256), 256, 0, st>>>(parts, prefix, B, tile_pair);
+    SIE_CHECK_LAUNCH();
+  } else {
+    if ((int)smem + 1024 > max_optin) {
+      sie_set_error("sie_corr_tau: Tp=%d needs %zu B of shared memory (> %d)", Tp, smem, max_optin);
+      return SIE_ERR_UNSUPPORTED;
+    }
+    cudaFuncSetAttribute(k_corr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long long slots = (long long)CTAS_PER_SM * sms;
+    int grid = (int)(max_items < slots ? max_items : slots);
+    k_corr_tiles<<<grid, NTHREADS, smem, st>>>(z, n_nodes, job_T, r_crit, prefix, table, B, ldn, Tp, R, tile_pair);
+    SIE_CHECK_LAUNCH();
+  }
+  k_tau_finalize<<<B, 256, 0, st>>>(tile_pair, prefix, tau_sum, tau_cnt, tau);
   SIE_CHECK_LAUNCH();
   return SIE_OK;
 }

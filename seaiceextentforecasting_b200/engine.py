@@ -155,7 +155,7 @@ class NetworkBatch:
                                    scratch.numel() * 8, _ptr(self.tau_sum[j0:]), _ptr(self.tau_cnt[j0:]),
                                    _ptr(self.tau[j0:]), shard_rank, shard_count, _stream())
         _lib.check(rc, "sie_corr_tau")
-        self.launches += 4
+        self.launches += 5
 
     def area_level(self, jr=None):
         """K3 + K4/K5."""

@@ -200,3 +200,51 @@ def test_row_sharded_tau_matches_unsharded_and_numpy(lib_built):
         P = stats.t.sf(R * np.sqrt(df / (1 - R ** 2)), df)
         ref = np.mean(R[(R >= 0) & (P < 0.01)])
     assert abs(tau_all - ref) <= 1e-9 * abs(ref)
+
+
+@pytest.mark.parametrize("X,Y,Ts,latlon", [(20, 22, [7, 12, 30, 42], False), (57, 57, [7, 25, 42], False),
+                                           (26, 90, [9, 42], True), (81, 81, [33], False)])
+def test_both_correlation_kernels_agree(lib_built, monkeypatch, X, Y, Ts, latlon):
+    """`sie_corr_tau` has two kernels (csrc/corr.cu): the tile kernel (default when R is stored) and the row-resident,
+    warp-specialised one (default for the tau-only pass).  Either can serve either mode (SIE_CORR_KERNEL): R must be
+    bitwise identical, bitwise symmetric with a NaN diagonal, the count identical and tau within 1e-12; R also matches
+    numpy's corrcoef of the detrended nodes to 1e-9 (ComplexNetworks.py:34-35)."""
+    import torch
+    from seaiceextentforecasting_b200.engine import NetworkBatch, h2d, r_crit_ttest
+    B, T, C = len(Ts), max(Ts), X * Y
+    data, _ = syn.make_field(X, Y, T, 21)
+    n_upper = int((~np.isnan(data).all(axis=2)).sum())
+    eng = NetworkBatch(X, Y, T, B, latlon=latlon, n_upper=n_upper, keep_R=True, max_areas=8)
+    fields = h2d(data.reshape(1, C, T))
+    jf = torch.zeros(B, dtype=torch.int32, device="cuda")
+    jT = torch.tensor(Ts, dtype=torch.int32, device="cuda")
+    rc = h2d(np.array([r_crit_ttest(t, 0.01) for t in Ts]))
+    eng.detrend_zscore(fields, jf, jT, True)
+    torch.cuda.synchronize()
+    N = eng.n_nodes.cpu().numpy()
+    out = {}
+    for kern in ("tiles", "rows"):
+        monkeypatch.setenv("SIE_CORR_KERNEL", kern)
+        eng.R.fill_(-7.0)
+        eng.corr_tau(rc, store_R=True)
+        torch.cuda.synchronize()
+        Rs = [eng.R[b, :N[b], :N[b]].cpu().numpy().copy() for b in range(B)]
+        stored = (eng.tau.cpu().numpy().copy(), eng.tau_cnt.cpu().numpy().copy())
+        eng.corr_tau(rc, store_R=False)
+        torch.cuda.synchronize()
+        out[kern] = (Rs, stored, (eng.tau.cpu().numpy().copy(), eng.tau_cnt.cpu().numpy().copy()))
+    for b in range(B):
+        a, c = out["tiles"][0][b], out["rows"][0][b]
+        assert np.array_equal(a, c, equal_nan=True)
+        assert np.array_equal(c, c.T, equal_nan=True) and np.isnan(np.diag(c)).all() and not (c == -7.0).any()
+    dtb = eng.dt[0, :, :Ts[0]].cpu().numpy()
+    nodes = eng.node_cell[0, :N[0]].cpu().numpy()
+    ref = np.corrcoef(dtb[nodes])
+    np.fill_diagonal(ref, np.nan)
+    m = ~np.isnan(ref)
+    assert np.max(np.abs(out["rows"][0][0][m] - ref[m])) <= 1e-9
+    for mode in (1, 2):
+        assert np.array_equal(out["tiles"][mode][1], out["rows"][mode][1])
+        np.testing.assert_allclose(out["tiles"][mode][0], out["rows"][mode][0], rtol=1e-12)
+    assert np.array_equal(out["rows"][1][1], out["rows"][2][1])
+    np.testing.assert_allclose(out["rows"][1][0], out["rows"][2][0], rtol=1e-12)
