@@ -2,9 +2,9 @@
 // Reference: detrend() north/June1st.py:179-194; node mask + np.corrcoef row centring
 // ComplexNetworks.py:32-34,:37; NaN sentinel cell ComplexNetworks.py:50-51.
 //
-// HBM-bound streaming: one warp per (job, cell); lane t walks the series with stride 32 so every warp
-// reads one contiguous T*8-byte run (<= 336 B at T=42) and writes one.  Algorithmic bytes: 16*C*T per
-// window (read raw, write residuals) + 8*N*Tp for the compacted z rows.
+// HBM-bound streaming: a CTA stages 128 consecutive series (one contiguous run) in shared memory with coalesced
+// loads, one thread per cell fits and removes its line from there, coalesced stores write the residuals.
+// Algorithmic bytes: 16*C*T per window (read raw, write residuals) + 8*N*Tp for the compacted z rows.
 #include "common.cuh"
 
 namespace {
@@ -15,82 +15,91 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) k_detrend_cells(
+constexpr int DT_CELLS = 128;     // cells (= threads) per CTA; their series are staged in shared memory
+
+// One thread per (job, cell).  The CTA's 128 series are one contiguous run of the field: it is copied to shared
+// memory with coalesced loads (row stride padded to an odd number of doubles, so the per-thread walks are
+// bank-conflict free), each thread fits and removes its own line with plain sequential sums (no shuffles, ~20
+// instructions per sample instead of a warp per 42-sample series), and the residuals go back with coalesced stores.
+__global__ void __launch_bounds__(DT_CELLS) k_detrend_cells(
     const double* __restrict__ fields, const int32_t* __restrict__ job_field,
-    const int32_t* __restrict__ job_T, int B, int C, int Tstride, int do_detrend,
+    const int32_t* __restrict__ job_T, int C, int Tstride, int ld, int do_detrend,
     double* __restrict__ dt, double* __restrict__ trend, int32_t* __restrict__ cell_flag,
     int32_t* __restrict__ first_nan_cell) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long total = (long long)B * C;
-  if (warp >= total) return;
-  const int b = (int)(warp / C);
-  const int c = (int)(warp - (long long)b * C);
+  extern __shared__ double sm[];          // [DT_CELLS][ld]
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * DT_CELLS;
+  const int nc = min(DT_CELLS, C - c0);
   const int T = job_T[b];
-  const double* src = fields + ((size_t)job_field[b] * C + c) * Tstride;
-  double* dst = dt + ((size_t)b * C + c) * Tstride;
-
-  // pass 1: NaN census, sum of y
-  double sy = 0.0;
-  int n_nan = 0;
-  for (int t = lane; t < T; t += 32) {
-    double v = src[t];
-    if (v != v) ++n_nan; else sy += v;
-  }
-  n_nan = __reduce_add_sync(0xffffffffu, n_nan);
-  if (n_nan > 0) {
-    // any NaN: linregress propagates NaN through the whole row (all-NaN cells are skipped and stay NaN)
-    if (lane == 0) {
+  const double* src = fields + ((size_t)job_field[b] * C + c0) * Tstride;
+  double* dst = dt + ((size_t)b * C + c0) * Tstride;
+  const int tid = threadIdx.x;
+  for (int r = tid >> 5; r < nc; r += DT_CELLS / 32)            // a warp per row: coalesced 8-byte loads
+    for (int t = tid & 31; t < Tstride; t += 32) sm[r * ld + t] = src[(size_t)r * Tstride + t];
+  __syncthreads();
+  if (tid < nc) {
+    double* y = sm + tid * ld;
+    const int c = c0 + tid;
+    // pass 1: NaN census, sum of y
+    double sy = 0.0;
+    int n_nan = 0;
+    for (int t = 0; t < T; ++t) {
+      const double v = y[t];
+      if (v != v) ++n_nan; else sy += v;
+    }
+    int flag;
+    if (n_nan > 0) {
+      // any NaN: linregress propagates NaN through the whole row (all-NaN cells are skipped and stay NaN)
       atomicMin(first_nan_cell + b, c);
-      cell_flag[(size_t)b * C + c] = 0;
+      flag = 0;
       if (trend) { trend[((size_t)b * C + c) * 2] = sie_nan(); trend[((size_t)b * C + c) * 2 + 1] = sie_nan(); }
-    }
-    if (do_detrend) {
-      for (int t = lane; t < Tstride; t += 32) dst[t] = sie_nan();
-    } else if (n_nan < T) {
-      // pass-through mode keeps a partially-NaN series visible: it is a node whose correlations are NaN
-      // (np.nanmax ignores the NaNs, np.corrcoef does not) -- ComplexNetworks.py:32-34
+      if (do_detrend) {
+        for (int t = 0; t < Tstride; ++t) y[t] = sie_nan();
+      } else if (n_nan < T) {
+        // pass-through mode keeps a partially-NaN series visible: it is a node whose correlations are NaN
+        // (np.nanmax ignores the NaNs, np.corrcoef does not) -- ComplexNetworks.py:32-34
+        double mx = -INFINITY;
+        for (int t = 0; t < T; ++t) { const double v = y[t]; if (v == v) mx = fmax(mx, v); }
+        flag = (fabs(mx) > 0.0) ? 1 : 0;
+      }
+    } else {
       double mx = -INFINITY;
-      for (int t = lane; t < T; t += 32) { double v = src[t]; if (v == v) mx = fmax(mx, v); }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      if (lane == 0) cell_flag[(size_t)b * C + c] = (fabs(mx) > 0.0) ? 1 : 0;
+      if (do_detrend) {
+        const double ym = sy / (double)T;
+        const double xm = 0.5 * (double)(T - 1);
+        double sxy = 0.0, sxx = 0.0;
+        for (int t = 0; t < T; ++t) {
+          const double dx = (double)t - xm;
+          sxy += dx * (y[t] - ym);
+          sxx += dx * dx;
+        }
+        sxy /= (double)T;
+        sxx /= (double)T;
+        const double slope = sxy / sxx;
+        const double icpt = ym - slope * xm;
+        for (int t = 0; t < T; ++t) {
+          // y - ((slope*t) + intercept): product rounded before the add, like the numpy expression
+          const double line = __dadd_rn(__dmul_rn(slope, (double)t), icpt);
+          const double r = __dsub_rn(y[t], line);
+          y[t] = r;
+          mx = fmax(mx, r);
+        }
+        for (int t = T; t < Tstride; ++t) y[t] = 0.0;
+        if (trend) {
+          trend[((size_t)b * C + c) * 2] = slope;
+          trend[((size_t)b * C + c) * 2 + 1] = icpt;
+        }
+      } else {
+        for (int t = 0; t < T; ++t) mx = fmax(mx, y[t]);
+      }
+      flag = (fabs(mx) > 0.0) ? 1 : 0;   // |nanmax| > 0
     }
-    return;
+    cell_flag[(size_t)b * C + c] = flag;
   }
-  double mx = -INFINITY;
-  if (do_detrend) {
-    sy = warp_sum(sy);
-    const double ym = sy / (double)T;
-    const double xm = 0.5 * (double)(T - 1);
-    double sxy = 0.0, sxx = 0.0;
-    for (int t = lane; t < T; t += 32) {
-      double dx = (double)t - xm;
-      sxy += dx * (src[t] - ym);
-      sxx += dx * dx;
-    }
-    sxy = warp_sum(sxy) / (double)T;
-    sxx = warp_sum(sxx) / (double)T;
-    const double slope = sxy / sxx;
-    const double icpt = ym - slope * xm;
-    for (int t = lane; t < T; t += 32) {
-      // y - ((slope*t) + intercept): product rounded before the add, like the numpy expression
-      double line = __dadd_rn(__dmul_rn(slope, (double)t), icpt);
-      double r = __dsub_rn(src[t], line);
-      dst[t] = r;
-      mx = fmax(mx, r);
-    }
-    for (int t = T + lane; t < Tstride; t += 32) dst[t] = 0.0;
-    if (trend && lane == 0) {
-      trend[((size_t)b * C + c) * 2] = slope;
-      trend[((size_t)b * C + c) * 2 + 1] = icpt;
-    }
-  } else {
-    for (int t = lane; t < T; t += 32) mx = fmax(mx, src[t]);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (lane == 0) cell_flag[(size_t)b * C + c] = (fabs(mx) > 0.0) ? 1 : 0;   // |nanmax| > 0
+  if (!do_detrend) return;
+  __syncthreads();
+  for (int r = tid >> 5; r < nc; r += DT_CELLS / 32)
+    for (int t = tid & 31; t < Tstride; t += 32) dst[(size_t)r * Tstride + t] = sm[r * ld + t];
 }
 
 // One CTA per job: order-preserving compaction of the node flags (ascending flat cell id, :37).
@@ -180,14 +189,18 @@ extern "C" int sie_detrend_zscore(const double* fields, const int32_t* job_field
   SIE_CHECK_ARG(Tp >= Tstride && (Tp % 4) == 0, "Tp must be >= Tstride and a multiple of 4");
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(first_nan_cell, 0x7f, sizeof(int32_t) * (size_t)B, st);
-  const long long warps = (long long)B * C;
-  const int wpb = 8;
-  k_detrend_cells<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, st>>>(
-      fields, job_field, job_T, B, C, Tstride, do_detrend, dt, trend, cell_node, first_nan_cell);
+  SIE_CHECK_ARG(B <= 65535, "at most 65535 jobs per call");
+  const int ld = Tp | 1;                                     // odd row stride (doubles) >= Tp >= Tstride
+  const size_t smem = sizeof(double) * (size_t)DT_CELLS * ld;
+  SIE_CHECK_ARG(smem <= 200 * 1024, "window too long for the shared-memory staging");
+  cudaFuncSetAttribute(k_detrend_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_detrend_cells<<<dim3((unsigned)((C + DT_CELLS - 1) / DT_CELLS), (unsigned)B), DT_CELLS, smem, st>>>(
+      fields, job_field, job_T, C, Tstride, ld, do_detrend, dt, trend, cell_node, first_nan_cell);
   SIE_CHECK_LAUNCH();
   k_compact_nodes<<<B, 1024, 0, st>>>(C, ldn, cell_node, node_cell, n_nodes, first_nan_cell, status);
   SIE_CHECK_LAUNCH();
   const long long zwarps = (long long)B * ldn;
+  const int wpb = 8;
   k_zrows<<<(unsigned)((zwarps + wpb - 1) / wpb), wpb * 32, 0, st>>>(dt, job_T, node_cell, n_nodes, B, C,
                                                                       Tstride, Tp, ldn, z);
   SIE_CHECK_LAUNCH();
