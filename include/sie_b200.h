@@ -73,7 +73,8 @@ int sie_detrend_zscore(const double* fields, const int32_t* job_field, const int
  * Replaces: np.corrcoef + fill_diagonal + t-test + mean      ComplexNetworks.py:34-35, :41-47
  * r_crit   [B]  host-computed critical correlation: P<alpha  <=>  R > r_crit
  * R        [B][ldn][ldn] or NULL (tau only; nothing but Z is read and 16 B/tile written)
- * tile_part [B][max_tiles][2] scratch for deterministic per-tile (sum,count) partials
+ * tile_part scratch of sie_corr_tau_scratch_bytes(B, ldn) bytes: tile table (32 B/tile), deterministic per-warp and
+ *           per-tile (sum,count) partials; a job range of a batch may use a disjoint slice
  * tau      [B]; tau_sum [B]; tau_cnt [B] (int64)   -- sums are over BOTH triangles like the reference
  * shard_rank/shard_count: tile-row bi is computed by the rank with bi % shard_count == shard_rank
  *     (multi-GPU row-block split; tau is then finished by the caller after an all-reduce of sum/cnt).

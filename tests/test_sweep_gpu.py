@@ -129,3 +129,27 @@ def test_sweep_hyper_grid_contains_the_script_settings(lib_built):
                 assert abs(g[key] - r[key]) <= 1e-9 * max(1.0, abs(r[key])), (p, key, g[key], r[key])
         hits += 1
     assert hits >= sw.P // 2
+
+
+def test_run_many_equals_run(lib_built):
+    """`run_many(n)` (bench.py's end-to-end loop: step i's results are read back and assembled while step i+1 is on the
+    device) yields, step by step, exactly what `run()` returns."""
+    from seaiceextentforecasting_b200.forecast import RetrospectiveSweep
+    fmin, fmax = 1993, 1996
+    Tfull = fmax - 1979 + 1
+    names = NORTH_INITS[1:3]
+    sic = {}
+    for i, name in enumerate(names):
+        sic[name], _ = syn.make_field(15, 15, Tfull, 310 + i, n_modes=50, noise=0.5, blob=(1.0, 2.5))
+    sie = dict(zip(CONFIGS[names[0]].regions, syn.make_sie(sic[names[0]], Tfull, 310)))
+    sw = RetrospectiveSweep(names, sic, sie, fmin, fmax, syn.make_psar(15, 15))
+    ref = sw.run()
+    raw_ref = sw.raw.copy()
+    outs = list(sw.run_many(3))
+    assert len(outs) == 3
+    assert np.array_equal(sw.raw.view(np.uint8), raw_ref.view(np.uint8))
+    for out in outs:
+        assert out.keys() == ref.keys()
+        for cfg in ref:
+            for k, v in ref[cfg].items():
+                assert np.array_equal(np.asarray(out[cfg][k]), np.asarray(v), equal_nan=True), (cfg, k)
