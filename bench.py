@@ -178,7 +178,7 @@ def run_reference(args):
                                        f"({cores} host cores); oracle port of the reference algorithm"},
             "e2e": {"value": value, "unit": "forecasts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -405,10 +405,22 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline_single()
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -422,6 +434,12 @@ def main():
                     help="skip the 25 km all-pairs correlation probe (second half of BASELINE.json's metric)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries ONE JSON line: libraries that write to file descriptor 1 (NCCL prints its version banner there when
+    # NCCL_DEBUG is set) are pointed at stderr, and the line goes to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -147,6 +147,8 @@ def test_run_many_equals_run(lib_built):
     raw_ref = sw.raw.copy()
     outs = list(sw.run_many(3))
     assert len(outs) == 3
+    sw.use_graph = True                      # the CUDA-graph replay of the step must give the same records
+    outs += list(sw.run_many(2))
     for f in ("fmean", "fvar", "sigma_f", "nlml", "g_ell", "g_sig", "n_pred", "expm_m", "expm_s", "info"):   # not the cycle counters
         assert np.array_equal(sw.raw[f], raw_ref[f], equal_nan=True), f
     for out in outs:
