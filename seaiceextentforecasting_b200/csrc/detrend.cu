@@ -34,8 +34,22 @@ __global__ void __launch_bounds__(DT_CELLS) k_detrend_cells(
   const double* src = fields + ((size_t)job_field[b] * C + c0) * Tstride;
   double* dst = dt + ((size_t)b * C + c0) * Tstride;
   const int tid = threadIdx.x;
-  for (int r = tid >> 5; r < nc; r += DT_CELLS / 32)            // a warp per row: coalesced 8-byte loads
-    for (int t = tid & 31; t < Tstride; t += 32) sm[r * ld + t] = src[(size_t)r * Tstride + t];
+  // the CTA's series are one contiguous run of nc * Tstride doubles: flat coalesced copy, 8 loads in flight per thread
+  // before the first shared-memory store (a load -> store loop pays one memory round trip per iteration)
+  const int total = nc * Tstride, pad = ld - Tstride;
+  for (int base = tid; base < total; base += 8 * DT_CELLS) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * DT_CELLS;
+      v[u] = idx < total ? src[idx] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * DT_CELLS;
+      if (idx < total) sm[idx + (idx / Tstride) * pad] = v[u];
+    }
+  }
   __syncthreads();
   if (tid < nc) {
     double* y = sm + tid * ld;
@@ -98,8 +112,19 @@ __global__ void __launch_bounds__(DT_CELLS) k_detrend_cells(
   }
   if (!do_detrend) return;
   __syncthreads();
-  for (int r = tid >> 5; r < nc; r += DT_CELLS / 32)
-    for (int t = tid & 31; t < Tstride; t += 32) dst[(size_t)r * Tstride + t] = sm[r * ld + t];
+  for (int base = tid; base < total; base += 8 * DT_CELLS) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * DT_CELLS;
+      v[u] = idx < total ? sm[idx + (idx / Tstride) * pad] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * DT_CELLS;
+      if (idx < total) dst[idx] = v[u];
+    }
+  }
 }
 
 // One CTA per job: order-preserving compaction of the node flags (ascending flat cell id, :37).
@@ -167,6 +192,17 @@ __global__ void __launch_bounds__(256) k_zrows(const double* __restrict__ dt, co
   }
   const int T = job_T[b];
   const double* src = dt + ((size_t)b * C + node_cell[(size_t)b * ldn + n]) * Tstride;
+  if (T <= 64) {
+    // the whole series sits in two registers per lane: one pass over memory, same summation order as the loops below
+    const double v0 = lane < T ? src[lane] : 0.0, v1 = lane + 32 < T ? src[lane + 32] : 0.0;
+    const double mean = warp_sum((0.0 + v0) + v1) / (double)T;
+    const double d0 = lane < T ? v0 - mean : 0.0, d1 = lane + 32 < T ? v1 - mean : 0.0;
+    const double inv = 1.0 / sqrt(warp_sum(fma(d1, d1, fma(d0, d0, 0.0))));   // q += d*d contracts to an FMA in the loop form
+    if (lane < Tp) zr[lane] = lane < T ? d0 * inv : 0.0;
+    if (lane + 32 < Tp) zr[lane + 32] = lane + 32 < T ? d1 * inv : 0.0;
+    for (int t = lane + 64; t < Tp; t += 32) zr[t] = 0.0;
+    return;
+  }
   double s = 0.0;
   for (int t = lane; t < T; t += 32) s += src[t];
   const double mean = warp_sum(s) / (double)T;
