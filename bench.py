@@ -389,7 +389,9 @@ def run_ours(args):
                        "l2": "working set per step ~7.8 GB (R matrices) >> 126 MB L2, no flush needed",
                        "schedule": (f"{len(sw.waves)} waves on separate streams, window-length edges T={list(sw.wave_T)}: "
                                     + "; ".join(f"{jr[1]-jr[0]} SIC networks + {pr[1]-pr[0]} GP problems" for (jr, sr, pr) in sw.waves)
-                                    + "; stage_ms / roofline timed in a separate single-wave pass") if sw.multi_wave else "single wave"},
+                                    + ("; each wave's GP = a launch for the SIC-only problems + one for the SST-reading ones" if sw.gp_sst else "")
+                                    + "; stage_ms / roofline timed in a separate single-wave pass; e2e loop = RetrospectiveSweep.run_many"
+                                      " (step i's D2H + host assemble overlap step i+1)") if sw.multi_wave else "single wave"},
             "e2e": {"value": e2e_value, "unit": "forecasts/s", "h2d_bytes_per_step": sw.h2d_bytes(),
                     "d2h_bytes_per_step": sw.d2h_bytes(), "ms_per_step": 1e3 * float(e2e_t.item()) / args.steps},
             "gpu_launches": args.steps * sw.kernel_launches(),

@@ -373,6 +373,8 @@ class RetrospectiveSweep:
         # the last wave = the shortest windows (networks finish early; their many small areas give the expensive
         # 100-160-predictor GP problems).  Every wave runs its chain on its own stream and its GP starts as soon as ITS
         # networks are done, overlapping the domain growth of the longer-window waves.
+        if os.environ.get("SIE_WAVE_T"):          # tuning override, e.g. SIE_WAVE_T=16 or 12,24
+            wave_T = tuple(int(x) for x in os.environ["SIE_WAVE_T"].split(","))
         edges = sorted({int(e) for e in (wave_T if isinstance(wave_T, (tuple, list)) else (wave_T,))}, reverse=True)
         self.wave_T = tuple(edges)
         T = plan.job_T
@@ -403,6 +405,22 @@ class RetrospectiveSweep:
         self.two_waves = self.multi_wave       # (name kept for callers)
         self.gp_wave = [GpBatch(max(1, pr[1] - pr[0]), max_pred=max_pred) for (_, _, pr) in self.waves[1:]] \
             if self.multi_wave else []
+        # Within a wave the problems that read no SST network come first: they only wait for the wave's SIC networks,
+        # the SST-reading ones (June) also for its SST networks, which finish later - two GP launches per wave instead
+        # of one that waits for everything.  Records are self-contained (y_off), so this is a permutation of
+        # plan.prob / plan.prob_meta; assemble() looks results up through prob_meta.
+        self.psplit = [pr[1] for (_, _, pr) in self.waves]
+        self.gp_sst = []
+        if self.multi_wave and self.use_sst and not os.environ.get("SIE_NO_GP_SPLIT"):
+            perm = np.arange(plan.P)
+            for w, (_, _, pr) in enumerate(self.waves):
+                idx = np.arange(pr[0], pr[1])
+                uses = plan.prob["job_sst"][idx] >= 0
+                perm[pr[0]:pr[1]] = np.concatenate([idx[~uses], idx[uses]])
+                self.psplit[w] = pr[0] + int((~uses).sum())
+            plan.prob = np.ascontiguousarray(plan.prob[perm])
+            plan.prob_meta = [plan.prob_meta[i] for i in perm]
+            self.gp_sst = [GpBatch(max(1, pr[1] - self.psplit[w]), max_pred=max_pred) for w, (_, _, pr) in enumerate(self.waves)]
         self._streams = None
         self._graph = None
         self.use_graph = bool(os.environ.get("SIE_GRAPH"))      # opt-in: see compute()
@@ -500,10 +518,13 @@ class RetrospectiveSweep:
         for (s1, s2) in self._streams:
             s1.wait_stream(main)
             s2.wait_stream(main)
-        # enqueue order = issue order: SIC chains from the longest windows (the critical path) to the shortest, then the
-        # SST chains from the shortest to the longest (measured best of the orders tried, tools/timeline.py)
-        seq = [("s", w) for w in range(nw)] + [("t", w) for w in range(nw - 1, -1, -1)]
+        sdone = [None] * nw                     # SST networks of wave w complete (None: the wave has none)
         done = [None] * nw
+        # enqueue order = issue order: SIC chains from the longest windows (the critical path) to the shortest, then
+        # the SST chains from the shortest to the longest (measured best of the orders tried, tools/timeline.py; splitting
+        # the chains into fronts K1+K2 / backs K3-K6 with high-priority fronts or explicit front-before-back events was
+        # 5-12 % slower in steady state: the long-window area CTAs must never wait for an SM)
+        seq = [("s", w) for w in range(nw)] + [("t", w) for w in range(nw - 1, -1, -1)]
         for kind, w in seq:
             jr, sr, pr = self.waves[w]
             if kind == "s":
@@ -516,21 +537,36 @@ class RetrospectiveSweep:
             elif self.sst is not None and sr[1] > sr[0]:
                 with torch.cuda.stream(self._streams[w][1]):
                     chain(f"sst{w}", self.sst, d["sst"], d["sst_field_idx"], d["sst_T"], d["sst_rcrit"], d["lat"], sr)
-        # GP of wave w: needs its own networks and those of the shorter-window waves (previous-year configurations)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    sdone[w] = ev
+        # GP of wave w: needs its own networks and those of the shorter-window waves (previous-year configurations);
+        # the problems that read SST networks are a second launch that also waits for those
+        gp_streams = self._streams
         for w in range(nw - 1, -1, -1):
             jr, sr, pr = self.waves[w]
-            if pr[1] <= pr[0]:
-                continue
-            st = self._streams[w][0]
-            with torch.cuda.stream(st):
-                for v in range(w, nw):
-                    st.wait_event(done[v])
-                    if self.sst is not None:
-                        st.wait_stream(self._streams[v][1])
-                mark(f"gp{w}.start")
-                gp = self.gp if w == 0 else self.gp_wave[w - 1]
-                gp.run(d["prob"], d["y"], self.sic, self.sst, pr, out=self.gp.out)
-                mark(f"gp{w}")
+            split = self.psplit[w] if self.gp_sst else pr[1]
+            if split > pr[0]:
+                st = gp_streams[w][0]
+                with torch.cuda.stream(st):
+                    for v in range(w, nw):
+                        st.wait_event(done[v])
+                        if not self.gp_sst and sdone[v] is not None:
+                            st.wait_event(sdone[v])
+                    mark(f"gp{w}.start")
+                    gp = self.gp if w == 0 else self.gp_wave[w - 1]
+                    gp.run(d["prob"], d["y"], self.sic, self.sst, (pr[0], split), out=self.gp.out)
+                    mark(f"gp{w}")
+            if pr[1] > split:
+                st = gp_streams[w][1]
+                with torch.cuda.stream(st):
+                    for v in range(w, nw):
+                        st.wait_event(done[v])
+                        if sdone[v] is not None:
+                            st.wait_event(sdone[v])
+                    mark(f"gps{w}.start")
+                    self.gp_sst[w].run(d["prob"], d["y"], self.sic, self.sst, (split, pr[1]), out=self.gp.out)
+                    mark(f"gps{w}")
         for (s1, s2) in self._streams:          # the step is complete on `main` once every wave has finished
             main.wait_stream(s1)
             main.wait_stream(s2)
@@ -559,8 +595,9 @@ class RetrospectiveSweep:
         if not self.multi_wave:
             return 12 * (2 if self.use_sst else 1) + 2
         n = 0
-        for (jr, sr, pr) in self.waves:
-            n += 12 * (jr[1] > jr[0]) + 12 * (self.use_sst and sr[1] > sr[0]) + 2 * (pr[1] > pr[0])
+        for w, (jr, sr, pr) in enumerate(self.waves):
+            split = self.psplit[w] if self.gp_sst else pr[1]
+            n += 12 * (jr[1] > jr[0]) + 12 * (self.use_sst and sr[1] > sr[0]) + 2 * (split > pr[0]) + 2 * (pr[1] > split)
         return int(n)
 
     def download(self):

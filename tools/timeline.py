@@ -11,6 +11,7 @@ sw.upload()
 for _ in range(3): sw.compute()
 torch.cuda.synchronize()
 for waves in (2, 1):
+    for _ in range(3): sw.compute(waves=None if waves == 2 else 1)       # steady state: the marked step is queued behind others
     e0 = torch.cuda.Event(enable_timing=True); e0.record()
     marks = []; sw.compute(marks, waves=waves)
     e1 = torch.cuda.Event(enable_timing=True); e1.record(); torch.cuda.synchronize()
