@@ -54,10 +54,14 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index, enabled=True):
+        # gpu_index: an index or a comma-separated list.  One poller (rank 0, all local GPUs) per job: every nvidia-smi
+        # query takes driver locks, so one poller per rank perturbs the launches of all ranks
+        self.idx, self.proc, self.lines, self.enabled = gpu_index, None, [], enabled
 
     def start(self):
+        if not self.enabled:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
@@ -71,6 +75,8 @@ class ClockSampler:
             self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self, t0, t1):
+        if not self.enabled:
+            return None
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -276,7 +282,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         sw.compute()
     sync_all()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local, enabled=(rank == 0))
     sampler.start()
     time.sleep(0.25)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -299,7 +305,11 @@ def run_ours(args):
     sync_all()
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     nf = torch.tensor([float(sw.n_forecasts)], dtype=torch.float64, device="cuda")
+    per_rank_ms = [dev_ms / args.steps]
     if world > 1:
+        allms = [torch.zeros_like(tmax) for _ in range(world)]
+        dist.all_gather(allms, tmax)
+        per_rank_ms = [float(t.item()) / args.steps for t in allms]     # rank r runs ensemble member r (different fields)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(nf, op=dist.ReduceOp.SUM)
     ms_per_step = float(tmax.item()) / args.steps
@@ -395,7 +405,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "forecasts/s", "h2d_bytes_per_step": sw.h2d_bytes(),
                     "d2h_bytes_per_step": sw.d2h_bytes(), "ms_per_step": 1e3 * float(e2e_t.item()) / args.steps},
             "gpu_launches": args.steps * sw.kernel_launches(),
-            "clocks": clocks,
+            "clocks": clocks, "per_rank_ms_per_step": per_rank_ms,
             "roofline": main_roof,
             "roofline_all": roof,
             "corr_25km": corr25,

@@ -1,5 +1,5 @@
 """Two north sweep steps (every kernel of the path launches twice per step and wave) -- the target of the ncu passes whose
-summaries are committed under profiles/ (see profiles/r01_kernels_v7_ncu.md for the exact command lines)."""
+summaries are committed under profiles/ (see profiles/r01_kernels_v9_ncu.md for the exact command lines)."""
 import sys, os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
