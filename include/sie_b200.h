@@ -59,6 +59,7 @@ int sie_device_info(int* sm_count, int* max_smem_optin, size_t* l2_bytes);
  * z           [B][ldn][Tp]  unit-norm centred rows, node-compacted, zero padded to Tp (Tp%4==0)
  * node_cell   [B][ldn], cell_node [B][C] (-1 = not a node), n_nodes [B], first_nan_cell [B] (-1 none)
  * status      [B] SIE_JOB_CAPACITY if n_nodes > ldn
+ * B <= 65535 jobs per call; Tp <= ~195 (128 series of Tp+1 doubles are staged in shared memory)
  */
 int sie_detrend_zscore(const double* fields, const int32_t* job_field, const int32_t* job_T,
                        int B, int C, int Tstride, int Tp, int do_detrend,
@@ -125,6 +126,8 @@ size_t sie_area_level_scratch_bytes(int B, int C);
  *     links, strength, strength map.
  * Replaces: Network.intra_links                                ComplexNetworks.py:283-326
  * scale      [C]  sqrt(area) or sqrt(cos(lat)) or ones (host computes the square root, :296-301)
+ * area_cells [B][C], area_start [B][max_areas+1], n_areas [B], label [B][C]: the outputs of sie_area_level (the member
+ *            list of an area is rank-sorted into ascending cell order on the device: numpy's reduction order)
  * anomaly    [B][max_areas][Tstride]; links [B][max_areas][max_areas]; strength [B][max_areas];
  * strengthmap [B][C] (NaN outside areas)
  */
