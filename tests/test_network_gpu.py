@@ -248,3 +248,49 @@ def test_both_correlation_kernels_agree(lib_built, monkeypatch, X, Y, Ts, latlon
         np.testing.assert_allclose(out["tiles"][mode][0], out["rows"][mode][0], rtol=1e-12)
     assert np.array_equal(out["rows"][1][1], out["rows"][2][1])
     np.testing.assert_allclose(out["rows"][1][0], out["rows"][2][0], rtol=1e-12)
+
+
+def test_full_size_25km_correlation_properties(lib_built, monkeypatch):
+    """BASELINE.json configs[3] at its full size (448x304 grid, T = 42, ~63 k nodes; the oracle cannot run it: R would be
+    32 GB) through size-independent properties of `sie_corr_tau` with R not stored: the (sum, count) partials of 8 row
+    shards add up to the unsharded result (count exactly), both kernels count the same pairs and agree on tau, and tau is
+    the mean of correlations that all exceed the critical value."""
+    import torch
+    from seaiceextentforecasting_b200.engine import NetworkBatch, h2d, r_crit_ttest
+    X, Y, T = 448, 304, 42
+    data, _ = syn.make_field(X, Y, T, 7)
+    n_upper = int((~np.isnan(data).any(axis=2)).sum())
+    eng = NetworkBatch(X, Y, T, 1, latlon=False, n_upper=n_upper, keep_R=False, max_areas=8)
+    f = h2d(data.reshape(1, X * Y, T))
+    jf = torch.zeros(1, dtype=torch.int32, device="cuda")
+    jT = torch.full((1,), T, dtype=torch.int32, device="cuda")
+    rcv = r_crit_ttest(T, 0.01)
+    rc = h2d(np.array([rcv]))
+    eng.detrend_zscore(f, jf, jT, True)
+    res = {}
+    for kern in ("rows", "tiles"):
+        monkeypatch.setenv("SIE_CORR_KERNEL", kern)
+        eng.corr_tau(rc, store_R=False)
+        torch.cuda.synchronize()
+        res[kern] = (eng.tau_sum.item(), eng.tau_cnt.item(), eng.tau.item())
+    monkeypatch.delenv("SIE_CORR_KERNEL")
+    N = int(eng.n_nodes.item())
+    assert N > 60000
+    s_all, c_all, tau_all = res["rows"]
+    assert res["tiles"][1] == c_all and abs(res["tiles"][0] - s_all) <= 1e-12 * s_all
+    assert 0 < c_all < N * (N - 1) and c_all % 2 == 0                      # both triangles
+    assert rcv < tau_all <= 1.0 and abs(tau_all - s_all / c_all) <= 1e-15
+    ss, cc = 0.0, 0
+    for r in range(8):
+        eng.corr_tau(rc, store_R=False, shard_rank=r, shard_count=8)
+        torch.cuda.synchronize()
+        ss += eng.tau_sum.item()
+        cc += eng.tau_cnt.item()
+    assert cc == c_all and abs(ss - s_all) <= 1e-12 * s_all
+    # a 512-node sample against numpy: the count of significant pairs inside the sample, from z rows of the device
+    idx = np.random.default_rng(0).choice(N, 512, replace=False)
+    z = eng.z[0, :N, :T].cpu().numpy()[np.sort(idx)]
+    Rs = z @ z.T
+    dtc = eng.dt[0].cpu().numpy()[eng.node_cell[0, :N].cpu().numpy()[np.sort(idx)], :T]
+    ref = np.corrcoef(dtc)
+    assert np.max(np.abs(Rs - ref)) <= 1e-9                                 # unit-norm rows reproduce np.corrcoef

@@ -156,3 +156,51 @@ def test_run_many_equals_run(lib_built):
         for cfg in ref:
             for k, v in ref[cfg].items():
                 assert np.array_equal(np.asarray(out[cfg][k]), np.asarray(v), equal_nan=True), (cfg, k)
+
+
+def test_full_size_north_sweep_invariants(lib_built):
+    """BASELINE.json configs[1] at its full size (the bench workload: 144 SIC 57x57 + 36 SST 26x90 networks, 432
+    forecasts; the oracle needs ~10 minutes for it) through size-independent properties: every network builds, areas
+    partition the labelled cells, R is bitwise symmetric with a NaN diagonal, node series are the scaled sums of their
+    member cells, every forecast but the known ill-conditioned July/Chukchi configuration is finite with positive variance,
+    and a second run reproduces the first bit for bit."""
+    import bench
+    from seaiceextentforecasting_b200 import _lib
+    from seaiceextentforecasting_b200.forecast import RetrospectiveSweep
+    w = bench.make_workload(0)
+    sw = RetrospectiveSweep(NORTH_INITS, w["sic"], w["sie"], bench.FMIN, bench.FMAX, w["psar"], w["sst"], w["lat"])
+    out = sw.run()
+    raw = sw.raw.copy()
+    assert len(raw) == 432
+    for eng in (sw.sic, sw.sst):
+        st = eng.status.cpu().numpy()
+        assert (st == _lib.SIE_JOB_OK).all()
+        na = eng.n_areas.cpu().numpy()
+        assert (na >= 2).all()
+        lab = eng.label.cpu().numpy()
+        starts = eng.area_start.cpu().numpy()
+        cells = eng.area_cells.cpu().numpy()
+        for b in (0, len(na) // 2, len(na) - 1):
+            assert starts[b, na[b]] == (lab[b] >= 0).sum()                  # areas partition the labelled cells
+            for a in (0, na[b] - 1):
+                mem = cells[b, starts[b, a]:starts[b, a + 1]]
+                assert (lab[b, mem] == a).all() and len(set(mem.tolist())) == len(mem)
+        N = int(eng.n_nodes[0].item())
+        R = eng.R[0, :N, :N].cpu().numpy()
+        assert np.array_equal(R, R.T, equal_nan=True) and np.isnan(np.diag(R)).all()
+        # node series of job 0, area 0: sequential row-major sum of dt * scale over the member cells (ComplexNetworks.py:303-306)
+        T0 = int(eng.job_T[0].item())
+        mem = np.sort(cells[0, starts[0, 0]:starts[0, 1]])
+        dt0 = eng.dt[0].cpu().numpy()
+        scale = (sw.dev["psar"] if eng is sw.sic else sw.dev["lat"]).cpu().numpy().reshape(-1)
+        acc = np.zeros(T0)
+        for c in mem:
+            acc = acc + dt0[c, :T0] * scale[c]
+        assert np.array_equal(eng.anomaly[0, 0, :T0].cpu().numpy(), acc)
+    bad = raw["info"] != 0
+    assert bad.sum() <= 2
+    ok = ~bad
+    assert np.isfinite(raw["fmean"][ok]).all() and (raw["fvar"][ok] > 0).all()
+    sw.run()
+    for f in ("fmean", "fvar", "nlml", "n_pred", "info"):
+        assert np.array_equal(sw.raw[f], raw[f], equal_nan=True), f
