@@ -283,6 +283,21 @@ class SweepPlan:
         self.y = np.concatenate(ys) if ys else np.zeros(0)
         self.P = len(probs)
 
+    def partition_sst(self, ranges):
+        """Stable partition of the problems inside every range (p0, p1): those that read no SST network first, the
+        SST-reading ones last.  Records are self-contained (job indices, y_off), so this only permutes `prob` and
+        `prob_meta` together; assemble() finds results through `prob_meta`.  Returns the split point of every range."""
+        perm = np.arange(self.P)
+        splits = []
+        for (p0, p1) in ranges:
+            idx = np.arange(p0, p1)
+            uses = self.prob["job_sst"][idx] >= 0
+            perm[p0:p1] = np.concatenate([idx[~uses], idx[uses]])
+            splits.append(int(p0 + (~uses).sum()))
+        self.prob = np.ascontiguousarray(self.prob[perm])
+        self.prob_meta = [self.prob_meta[i] for i in perm]
+        return splits
+
     def assemble(self, raw, meta=None):
         """-> {config: {region_fmean / _fvar / _fmean_rt: array(years)}} like the reference's GPR dict
         (June1st_retro.py:284-290, rounded to 3 d.p.), the un-rounded values under '<region>_raw_*'.
@@ -412,14 +427,7 @@ class RetrospectiveSweep:
         self.psplit = [pr[1] for (_, _, pr) in self.waves]
         self.gp_sst = []
         if self.multi_wave and self.use_sst and not os.environ.get("SIE_NO_GP_SPLIT"):
-            perm = np.arange(plan.P)
-            for w, (_, _, pr) in enumerate(self.waves):
-                idx = np.arange(pr[0], pr[1])
-                uses = plan.prob["job_sst"][idx] >= 0
-                perm[pr[0]:pr[1]] = np.concatenate([idx[~uses], idx[uses]])
-                self.psplit[w] = pr[0] + int((~uses).sum())
-            plan.prob = np.ascontiguousarray(plan.prob[perm])
-            plan.prob_meta = [plan.prob_meta[i] for i in perm]
+            self.psplit = plan.partition_sst([pr for (_, _, pr) in self.waves])
             self.gp_sst = [GpBatch(max(1, pr[1] - self.psplit[w]), max_pred=max_pred) for w, (_, _, pr) in enumerate(self.waves)]
         self._streams = None
         self._graph = None

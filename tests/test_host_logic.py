@@ -233,3 +233,34 @@ def test_row_sharded_tau_allreduce_two_ranks():
     for p in procs:
         p.join(timeout=60)
     assert ok
+
+
+def test_partition_sst_permutes_problems_and_meta_together():
+    """RetrospectiveSweep launches each wave's GP twice (problems that read no SST network / those that do):
+    SweepPlan.partition_sst reorders the records inside the wave ranges; the result lookup through prob_meta must not
+    notice."""
+    from seaiceextentforecasting_b200.forecast import GP_RESULT_DTYPE
+    p = SweepPlan(NORTH_INITS, _sie(), 1985, 2020)
+    q = SweepPlan(NORTH_INITS, _sie(), 1985, 2020)
+    T = q.job_T[q.prob["job_sic"]]
+    cut = int((T > 12).sum())
+    ranges = [(0, cut), (cut, q.P)]
+    splits = q.partition_sst(ranges)
+    assert q.P == p.P == 432 and sorted(q.prob_meta) == sorted(p.prob_meta)
+    for (p0, p1), sp in zip(ranges, splits):
+        assert p0 < sp < p1
+        assert (q.prob["job_sst"][p0:sp] < 0).all() and (q.prob["job_sst"][sp:p1] >= 0).all()
+        assert (np.diff(q.job_T[q.prob["job_sic"][p0:sp]]) <= 0).all()        # stable: still longest windows first
+    where = {m: i for i, m in enumerate(p.prob_meta)}
+    for i, m in enumerate(q.prob_meta):                                       # record i of q is record where[m] of p
+        assert q.prob[i] == p.prob[where[m]]
+    # results written in either order assemble to the same dict
+    rng = np.random.default_rng(0)
+    raw_p = np.zeros(p.P, dtype=GP_RESULT_DTYPE)
+    raw_p["fmean"], raw_p["fvar"] = rng.normal(size=p.P), rng.uniform(0.1, 1.0, size=p.P)
+    raw_q = raw_p[[where[m] for m in q.prob_meta]]
+    a, b = p.assemble(raw_p), q.assemble(raw_q)
+    assert a.keys() == b.keys()
+    for cfg in a:
+        for k in a[cfg]:
+            assert np.array_equal(np.asarray(a[cfg][k]), np.asarray(b[cfg][k]), equal_nan=True), (cfg, k)
