@@ -36,15 +36,24 @@ WORKLOAD = ("north retrospective sweep 1985-2020 x June/July/August/September in
 
 
 def make_workload(member=0):
-    """Synthetic inputs of BASELINE.json configs[1]; `member` perturbs the seeds (ensemble member)."""
+    """Synthetic inputs of BASELINE.json configs[1].  Member 0 is the base realisation; member m > 0 is the perturbed-SIC
+    ensemble member of SURVEY.md 8(d) / BASELINE.json configs[4]: base field + 0.05 * N(0,1) with seed base_seed + m
+    (concentrations stay in [0, 1], saturated samples and land stay as they are; the SIE targets are shared)."""
     from seaiceextentforecasting_b200 import synthetic as syn
     from seaiceextentforecasting_b200.config import CONFIGS, NORTH_INITS
     sic = {}
     for i, name in enumerate(NORTH_INITS):
-        sic[name], _ = syn.make_field(57, 57, TFULL, 1000 + 17 * member + i)
-    sie = dict(zip(CONFIGS["north_june"].regions, syn.make_sie(sic["north_september"], TFULL, 1000 + member)))
-    sst, _ = syn.make_field(26, 90, TFULL, 2000 + member, latlon=True, saturate=False, n_modes=60, noise=0.6,
+        sic[name], _ = syn.make_field(57, 57, TFULL, 1000 + i)
+    sie = dict(zip(CONFIGS["north_june"].regions, syn.make_sie(sic["north_september"], TFULL, 1000)))
+    sst, _ = syn.make_field(26, 90, TFULL, 2000, latlon=True, saturate=False, n_modes=60, noise=0.6,
                             blob=(2.0, 5.0))
+    if member > 0:
+        rng = np.random.default_rng(5000 + member)
+        for name in NORTH_INITS:
+            f = sic[name]
+            inside = (f > 0.0) & (f < 1.0)              # NaN (land) compares False
+            sic[name] = np.where(inside, np.clip(f + 0.05 * rng.standard_normal(f.shape), 0.0, 1.0), f)
+        sst = sst + 0.05 * rng.standard_normal(sst.shape)      # NaN land stays NaN
     return dict(sic=sic, sie=sie, sst=sst, psar=syn.make_psar(57, 57), lat=syn.make_lat_grid(26, 90))
 
 
