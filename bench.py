@@ -405,6 +405,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "grid": "57x57 SIC + 26x90 SST", "years": [FMIN, FMAX],
                        "ensemble_members": world, "parallelism": f"task-parallel x{world} (one member per GPU)",
+                       "members": "rank 0 = base realisation, rank r = base + 0.05*N(0,1) (perturbed-SIC ensemble member r)",
                        "l2": "working set per step ~7.8 GB (R matrices) >> 126 MB L2, no flush needed",
                        "schedule": (f"{len(sw.waves)} waves on separate streams, window-length edges T={list(sw.wave_T)}: "
                                     + "; ".join(f"{jr[1]-jr[0]} SIC networks + {pr[1]-pr[0]} GP problems" for (jr, sr, pr) in sw.waves)
