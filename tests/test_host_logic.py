@@ -264,3 +264,21 @@ def test_partition_sst_permutes_problems_and_meta_together():
     for cfg in a:
         for k in a[cfg]:
             assert np.array_equal(np.asarray(a[cfg][k]), np.asarray(b[cfg][k]), equal_nan=True), (cfg, k)
+
+
+def test_bench_ensemble_members_are_perturbations_of_the_base():
+    """bench.py: rank r runs ensemble member r = base + 0.05 N(0,1); member 0 is the base realisation, the
+    land mask and the saturated samples never change, concentrations stay in [0, 1]."""
+    import bench
+    w0, w0b, w3 = bench.make_workload(0), bench.make_workload(0), bench.make_workload(3)
+    for name in w0["sic"]:
+        a, b = w0["sic"][name], w3["sic"][name]
+        assert np.array_equal(a, w0b["sic"][name], equal_nan=True)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        sat = (a == 0.0) | (a == 1.0)
+        assert np.array_equal(a[sat], b[sat])
+        assert np.nanmin(b) >= 0.0 and np.nanmax(b) <= 1.0
+        d = (b - a)[~np.isnan(a) & ~sat]
+        assert 0.03 < d.std() < 0.06 and abs(d.mean()) < 1e-3
+    assert np.array_equal(np.isnan(w0["sst"]), np.isnan(w3["sst"]))
+    assert all(np.array_equal(w0["sie"][k], w3["sie"][k]) for k in w0["sie"])
