@@ -41,7 +41,7 @@ extern "C" {
 
 #define SIE_AREA_WORK 32        /* uint64 profiling counters per job written by sie_area_level */
 
-int sie_abi_version(void);
+int sie_abi_version(void);          /* 2 */
 const char* sie_last_error(void);
 /* device facts used by the host layer for launch sizing; returns 0 on success */
 int sie_device_info(int* sm_count, int* max_smem_optin, size_t* l2_bytes);
@@ -79,12 +79,18 @@ int sie_detrend_zscore(const double* fields, const int32_t* job_field, const int
  * tau      [B]; tau_sum [B]; tau_cnt [B] (int64)   -- sums are over BOTH triangles like the reference
  * shard_rank/shard_count: tile-row bi is computed by the rank with bi % shard_count == shard_rank
  *     (multi-GPU row-block split; tau is then finished by the caller after an all-reduce of sum/cnt).
+ * kernel   SIE_CORR_AUTO: the 128x64 tile kernel when R is stored, the row-resident warp-specialised kernel for the
+ *          tau-only pass (R == NULL); SIE_CORR_TILES / SIE_CORR_ROWS force one (both serve both modes and agree
+ *          bit for bit).  There is no environment variable or other hidden state behind the choice.
  */
+#define SIE_CORR_AUTO 0
+#define SIE_CORR_TILES 1
+#define SIE_CORR_ROWS 2
 int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32_t* job_T, const double* r_crit,
                  int B, int ldn, int Tp, double* R,
                  double* tile_part, size_t tile_part_bytes,
                  double* tau_sum, int64_t* tau_cnt, double* tau,
-                 int shard_rank, int shard_count, void* stream);
+                 int shard_rank, int shard_count, int kernel, void* stream);
 size_t sie_corr_tau_scratch_bytes(int B, int ldn);
 
 /* K3  local stencil: correlation of every node with its 4 von-Neumann neighbours (up,down,left,right;
@@ -165,7 +171,7 @@ typedef struct SieGpProblem {
 
 typedef struct SieGpResult {
   double fmean, fvar, sigma_f, nlml, g_ell, g_sig;
-  int32_t n_pred, expm_m, expm_s, info; /* info: 0 ok, k>0 Cholesky failed at pivot k, -1 no predictors, -2 capacity */
+  int32_t n_pred, expm_m, expm_s, info; /* info: 0 ok, k>0 Cholesky failed at pivot k (LinAlgError), -1 fewer than 2 predictors selected (the reference raises IndexError / ValueError), -2 capacity */
   int64_t cycles_total, cycles_expm;    /* SM cycles this problem took (whole / expm only), for profiling */
 } SieGpResult;
 

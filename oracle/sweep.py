@@ -50,9 +50,14 @@ def build_network(field, year, latlon, weight, significance=0.01):
     return net.V, net.anomaly, net.tau
 
 
-def run_job(cfg, year, sic_field, psar, sie_dt, sie_trend, fmin, sst_field=None, sst_lat=None):
+FAILS = (IndexError, ValueError, np.linalg.LinAlgError)   # what forecast() raises: no / one predictor, non-SPD K
+
+
+def run_job(cfg, year, sic_field, psar, sie_dt, sie_trend, fmin, sst_field=None, sst_lat=None, record_failures=False):
     """All three regional forecasts of one (config, target year): the network build(s) plus forecast().
-    `cfg` is a seaiceextentforecasting_b200.config.ForecastConfig (plain data)."""
+    `cfg` is a seaiceextentforecasting_b200.config.ForecastConfig (plain data).  `record_failures`: a region on
+    which forecast() raises (the reference aborts the whole script there) becomes a record of NaNs with
+    `failed = <exception name>` instead of propagating."""
     ny = year - 1 if cfg.prev_year_network else year
     V, anoms, tau = build_network(sic_field, ny, False, psar)
     sst_anoms = None
@@ -66,8 +71,15 @@ def run_job(cfg, year, sic_field, psar, sie_dt, sie_trend, fmin, sst_field=None,
         else:
             y = sie_dt[reg][row, 0:year - FIRST_YEAR]
         slope, icpt = sie_trend[reg][row]
-        r = ogp.forecast_one(y, anoms, sst_anoms, _RULES[cfg.rule[k]], cfg.alpha, cfg.zscore, cfg.ell[k], cfg.sig[k],
-                             slope, icpt, year - FIRST_YEAR)
+        try:
+            r = ogp.forecast_one(y, anoms, sst_anoms, _RULES[cfg.rule[k]], cfg.alpha, cfg.zscore, cfg.ell[k], cfg.sig[k],
+                                 slope, icpt, year - FIRST_YEAR)
+            r["failed"] = None
+        except FAILS as e:
+            if not record_failures:
+                raise
+            r = dict(fmean=np.nan, fvar=np.nan, sigma_f=np.nan, nlml=np.nan, cond=np.nan, n_pred=-1,
+                     failed=type(e).__name__)
         lineT = (np.arange(year - FIRST_YEAR + 1) * slope) + icpt
         r["fmean_rt"] = r["fmean"] + lineT[-1]
         r["n_areas"] = len(V)
@@ -75,8 +87,9 @@ def run_job(cfg, year, sic_field, psar, sie_dt, sie_trend, fmin, sst_field=None,
     return out, V
 
 
-def retro_sweep(cfgs, sic_fields, sie, fmin, fmax, psar, sst_field=None, sst_lat=None):
-    """-> {config: {region+'_fmean'|'_fvar'|'_fmean_rt': array(years)}} un-rounded, plus V per network year."""
+def retro_sweep(cfgs, sic_fields, sie, fmin, fmax, psar, sst_field=None, sst_lat=None, record_failures=False):
+    """-> {config: {region+'_fmean'|'_fvar'|'_fmean_rt': array(years)}} un-rounded, plus V per network year (and, with
+    `record_failures`, region+'_failed': list of exception names / None and region+'_cond')."""
     out = {}
     for cfg in cfgs:
         tables = {reg: sie_tables(sie[reg], fmin, fmax) for reg in cfg.regions}
@@ -84,13 +97,17 @@ def retro_sweep(cfgs, sic_fields, sie, fmin, fmax, psar, sst_field=None, sst_lat
         sie_trend = {reg: tables[reg][1] for reg in cfg.regions}
         g = out.setdefault(cfg.name, {"V": {}})
         for reg in cfg.regions:
-            for suf in ("_fmean", "_fvar", "_fmean_rt"):
+            for suf in ("_fmean", "_fvar", "_fmean_rt", "_cond"):
                 g[reg + suf] = np.zeros(fmax - fmin + 1)
+            g[reg + "_failed"] = [None] * (fmax - fmin + 1)
         for year in range(fmin, fmax + 1):
-            res, V = run_job(cfg, year, sic_fields[cfg.name], psar, sie_dt, sie_trend, fmin, sst_field, sst_lat)
+            res, V = run_job(cfg, year, sic_fields[cfg.name], psar, sie_dt, sie_trend, fmin, sst_field, sst_lat,
+                             record_failures)
             g["V"][year - 1 if cfg.prev_year_network else year] = V
             for k, reg in enumerate(cfg.regions):
                 g[reg + "_fmean"][year - fmin] = res[k]["fmean"]
                 g[reg + "_fvar"][year - fmin] = res[k]["fvar"]
                 g[reg + "_fmean_rt"][year - fmin] = res[k]["fmean_rt"]
+                g[reg + "_cond"][year - fmin] = res[k]["cond"]
+                g[reg + "_failed"][year - fmin] = res[k]["failed"]
     return out

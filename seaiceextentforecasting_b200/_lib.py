@@ -10,6 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsie_b200.so")
 
 SIE_JOB_OK, SIE_JOB_NO_NAN_CELL, SIE_JOB_FEW_AREAS, SIE_JOB_CAPACITY = 0, 1, 2, 3
+SIE_CORR_AUTO, SIE_CORR_TILES, SIE_CORR_ROWS = 0, 1, 2
+ABI_VERSION = 2
 SIE_AREA_WORK = 32   # uint64 profiling counters per job (include/sie_b200.h)
 
 c_i32 = C.c_int32
@@ -36,7 +38,7 @@ _SIGS = {
     "sie_detrend_zscore": (C.c_int, [c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p, c_p,
                                      c_p, c_p, c_p, c_p, c_p, C.c_int, c_p]),
     "sie_corr_tau": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, c_p, c_p, c_sz, c_p, c_p, c_p,
-                               C.c_int, C.c_int, c_p]),
+                               C.c_int, C.c_int, C.c_int, c_p]),
     "sie_corr_tau_scratch_bytes": (c_sz, [C.c_int, C.c_int]),
     "sie_corr_stencil": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p]),
     "sie_area_level": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -75,6 +77,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.sie_abi_version() != ABI_VERSION:
+        raise SieError(f"{LIB_PATH} has ABI version {lib.sie_abi_version()}, this package needs {ABI_VERSION}: rebuild")
     _lib = lib
     return lib
 

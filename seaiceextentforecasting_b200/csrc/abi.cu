@@ -1,6 +1,7 @@
 // Error reporting and device facts for libsie_b200.
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -12,18 +13,59 @@ void sie_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-extern "C" int sie_abi_version(void) { return 1; }
+// Device facts are read once per device and cached: the entry points only enqueue kernels, they do not query the
+// driver or set function attributes on every call (a sweep step enqueues ~60 kernels).
+static SieDevice g_dev[SIE_MAX_DEVICES];
+static std::mutex g_dev_mutex;
+
+const SieDevice* sie_device(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= SIE_MAX_DEVICES) {
+    (void)cudaGetLastError();
+    sie_set_error("no CUDA device (or device ordinal >= %d)", SIE_MAX_DEVICES);
+    return nullptr;
+  }
+  SieDevice* d = &g_dev[dev];
+  if (!d->ready) {
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    if (!d->ready) {
+      int v = 0;
+      d->ordinal = dev;
+      cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); d->sm_count = v;
+      cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); d->max_smem_optin = v;
+      cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev); d->smem_per_sm = v;
+      cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev); d->l2_bytes = (size_t)v;
+      for (int i = 0; i < SIE_ATTR_SLOTS; ++i) d->attr_smem[i] = -1;
+      d->ready = 1;
+    }
+  }
+  return d;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when the requested size exceeds what this kernel (slot) was
+// last given on this device.
+int sie_ensure_smem(const SieDevice* d, int slot, const void* func, size_t bytes) {
+  SieDevice* m = const_cast<SieDevice*>(d);
+  if ((long long)bytes <= (long long)m->attr_smem[slot]) return SIE_OK;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  if ((long long)bytes <= (long long)m->attr_smem[slot]) return SIE_OK;
+  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    sie_set_error("cudaFuncSetAttribute(%zu B of dynamic shared memory) failed: %s", bytes,
+                  cudaGetErrorString(cudaGetLastError()));
+    return SIE_ERR_LAUNCH;
+  }
+  m->attr_smem[slot] = (long long)bytes;
+  return SIE_OK;
+}
+
+extern "C" int sie_abi_version(void) { return 2; }
 extern "C" const char* sie_last_error(void) { return g_err; }
 
 extern "C" int sie_device_info(int* sm_count, int* max_smem_optin, size_t* l2_bytes) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) {
-    sie_set_error("sie_device_info: no CUDA device");
-    return SIE_ERR_LAUNCH;
-  }
-  int v = 0;
-  if (sm_count) { cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); *sm_count = v; }
-  if (max_smem_optin) { cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev); *max_smem_optin = v; }
-  if (l2_bytes) { cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev); *l2_bytes = (size_t)v; }
+  const SieDevice* d = sie_device();
+  if (!d) return SIE_ERR_LAUNCH;
+  if (sm_count) *sm_count = d->sm_count;
+  if (max_smem_optin) *max_smem_optin = d->max_smem_optin;
+  if (l2_bytes) *l2_bytes = d->l2_bytes;
   return SIE_OK;
 }

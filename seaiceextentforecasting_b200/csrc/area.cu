@@ -24,22 +24,41 @@
 //    block for every candidate and round.
 // Integer state and the per-area tables live in shared memory; arrays that do not fit (big grids) fall back to
 // global scratch one by one.  No roofline fraction is claimed for this kernel; see DESIGN.md.
+//
+// Throughput (the metric is forecasts/s over many networks, not the latency of one): the grid is PERSISTENT -- CTAs
+// pop jobs from an atomic queue in index order (the host puts the long-window, i.e. slowest, networks first: LPT), so
+// an SM is never idle while jobs remain and the global scratch is per CTA, not per job.  Three instantiations:
+//   <256 threads, 16-bit indices>  small grids (57x57 SIC, 26x90 SST): ~105 KB of shared memory and 128 registers,
+//                                  so TWO latency-bound chains share an SM and overlap each other's stalls;
+//   <512 threads, 16-bit indices>  mid-size grids (81x81): every array still on chip, one CTA per SM;
+//   <512 threads, 32-bit indices>  anything larger (25 km): arrays evicted to global scratch as needed.
+#include <type_traits>
 #include "common.cuh"
 
 namespace {
 
-constexpr int NT = 512;
-constexpr int NW = NT / 32;
-constexpr int NG = NT / 8;          // 8-lane groups per CTA
-constexpr int FCAP = 256;          // frontier slots with incremental state: slot s is owned by thread s
-constexpr int BKW = NW - 1;        // the warp that updates integer state and initialises new slots
 constexpr int LEAF = 128;          // numpy's pairwise block size
 constexpr int DCAP_MAX = 1024;     // rows/cols of the dense best-area sub-matrix
 constexpr int MAXCH = 32;          // neighbour areas evaluated per chunk of a merge round
-constexpr uint32_t NOKEY = 0xffffffffu;
 constexpr unsigned long long NOKEY64 = ~0ull;
 constexpr unsigned FULL = 0xffffffffu;
-static_assert(FCAP <= NT - 32, "slot threads and the bookkeeping warp must be distinct");
+
+// NT threads; FCAP frontier slots with incremental state (slot s is owned by thread s); the last warp updates the
+// integer state and initialises new slots.  IT = type of the per-cell index arrays and the per-area tables.
+template <int NT_, typename IT_>
+struct AreaCfg {
+  static constexpr int NT = NT_;
+  static constexpr int NW = NT_ / 32;
+  static constexpr int NG = NT_ / 8;                  // 8-lane groups per CTA
+  static constexpr int FCAP = NT_ >= 512 ? 256 : 192;
+  static constexpr int BKW = NW - 1;
+  static constexpr int CTAS = NT_ >= 512 ? 1 : 2;     // co-resident CTAs per SM the launch bounds allow
+  using IT = IT_;
+  using FK = typename std::conditional<sizeof(IT_) == 2, uint16_t, uint32_t>::type;   // frontier key
+  static constexpr FK NOKEY = (FK)~(FK)0;
+  static constexpr int DSHIFT = sizeof(IT_) == 2 ? 14 : 28;   // key = direction << DSHIFT | list position
+  static_assert(FCAP <= NT - 32, "slot threads and the bookkeeping warp must be distinct");
+};
 
 // which arrays live in global scratch instead of shared memory (bit set = global)
 enum : int { PL_LAB = 1, PL_FKEY = 2, PL_FLIST = 4, PL_HN = 8, PL_HC = 16, PL_CNL = 32, PL_KNL = 64, PL_AREA = 128 };
@@ -47,44 +66,47 @@ enum : int { PL_LAB = 1, PL_FKEY = 2, PL_FLIST = 4, PL_HN = 8, PL_HC = 16, PL_CN
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline size_t rm_cap(int C) { return (size_t)4 * C + 1024; }
 __host__ __device__ inline int d_cap(int C) { return C < DCAP_MAX ? C : DCAP_MAX; }
-__host__ __device__ inline size_t area_tab_bytes(int MA) {       // 12 int32 tables + okey + stat
-  return 12 * align_up(sizeof(int32_t) * (size_t)(MA + 1), 16) + 2 * align_up(sizeof(double) * (size_t)MA, 16);
+__host__ __device__ inline size_t area_tab_bytes(int MA, size_t isz) {       // 12 integer tables + okey + stat
+  return 12 * align_up(isz * (size_t)(MA + 1), 16) + 2 * align_up(sizeof(double) * (size_t)MA, 16);
 }
 __host__ __device__ inline size_t self_cap(int C) { return (size_t)2 * C + 64; }
-__host__ __device__ inline size_t slot_bytes() { return sizeof(double) * (18 * FCAP) + sizeof(int32_t) * 2 * FCAP; }
-__host__ __device__ inline size_t scratch_per_job(int C, int MA) {
+__host__ __device__ inline size_t slot_bytes(int fcap) { return sizeof(double) * (18 * (size_t)fcap) + sizeof(int32_t) * 2 * (size_t)fcap; }
+constexpr size_t QUEUE_BYTES = 256;                         // head of the scratch: the job-queue counter
+__host__ __device__ inline size_t scratch_per_cta(int C, int MA) {
   size_t s = 0;
   s += align_up(sizeof(int32_t) * (size_t)C, 256);          // s1_cells
   s += align_up(sizeof(int32_t) * (size_t)7 * C, 256);      // fallback for the shared-memory integer arrays
   s += align_up(sizeof(double) * rm_cap(C), 256);           // rowmean
   s += align_up(sizeof(double) * ((size_t)d_cap(C) * d_cap(C) + 128), 256);   // dmat (+ read-ahead pad)
-  s += align_up(area_tab_bytes(MA), 256);                   // fallback for the per-area tables
+  s += align_up(area_tab_bytes(MA, sizeof(int32_t)), 256);  // fallback for the per-area tables
   s += align_up(sizeof(double) * self_cap(C), 256);         // cached self row means of candidate areas
   return s;
 }
 
+template <typename IT>
 struct AreaTabs {       // per step-1 area (segment); merged areas are chains of segments
-  int32_t *a_start, *a_len, *seg_next, *tail, *size, *fin, *nlist;
-  int32_t *xoff, *xep, *xrows;     // step 2: column offset of the area's cross block in D, epoch it belongs to, best rows filled
-  int32_t *self_off, *self_sz;     // step 2: cached self row means (offset into selfbuf; valid when self_sz == size)
+  IT *a_start, *a_len, *seg_next, *tail, *size, *fin, *nlist;
+  IT *xoff, *xep, *xrows;          // step 2: column offset of the area's cross block in D, epoch it belongs to, best rows filled
+  IT *self_off, *self_sz;          // step 2: cached self row means (offset into selfbuf; valid when self_sz == size)
   unsigned long long* okey;
   double* stat;
 };
-__device__ inline AreaTabs carve_tabs(unsigned char* p, int MA) {
-  AreaTabs t;
+template <typename IT>
+__device__ inline AreaTabs<IT> carve_tabs(unsigned char* p, int MA) {
+  AreaTabs<IT> t;
   auto take = [&](size_t bytes) { unsigned char* r = p; p += align_up(bytes, 16); return r; };
-  t.a_start = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  t.a_len = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  t.seg_next = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  t.tail = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  t.size = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  t.fin = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  t.nlist = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  t.xoff = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  t.xep = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  t.xrows = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  t.self_off = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
-  t.self_sz = (int32_t*)take(sizeof(int32_t) * (size_t)(MA + 1));
+  t.a_start = (IT*)take(sizeof(IT) * (size_t)(MA + 1));
+  t.a_len = (IT*)take(sizeof(IT) * (size_t)(MA + 1));
+  t.seg_next = (IT*)take(sizeof(IT) * (size_t)(MA + 1));
+  t.tail = (IT*)take(sizeof(IT) * (size_t)(MA + 1));
+  t.size = (IT*)take(sizeof(IT) * (size_t)(MA + 1));
+  t.fin = (IT*)take(sizeof(IT) * (size_t)(MA + 1));
+  t.nlist = (IT*)take(sizeof(IT) * (size_t)(MA + 1));
+  t.xoff = (IT*)take(sizeof(IT) * (size_t)(MA + 1));
+  t.xep = (IT*)take(sizeof(IT) * (size_t)(MA + 1));
+  t.xrows = (IT*)take(sizeof(IT) * (size_t)(MA + 1));
+  t.self_off = (IT*)take(sizeof(IT) * (size_t)(MA + 1));
+  t.self_sz = (IT*)take(sizeof(IT) * (size_t)(MA + 1));
   t.okey = (unsigned long long*)take(sizeof(double) * (size_t)MA);
   t.stat = (double*)take(sizeof(double) * (size_t)MA);
   return t;
@@ -151,7 +173,7 @@ __device__ __forceinline__ Rec warp_arg(const Rec& r) {
 struct RecSlot { unsigned long long ord, pri; uint32_t a, b, pad0, pad1; };   // 32 bytes
 // CTA-wide argmax; every thread returns the same winner.  `slots` is shared scratch [2][NW]; `par` alternates so
 // the next call never overwrites records a slow warp is still reading (one barrier per call).
-template <int PW>
+template <int PW, int NW>
 __device__ __forceinline__ Rec block_arg(const Rec& v, RecSlot* slots, int& par) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Rec w = warp_arg<PW>(v);
@@ -164,17 +186,21 @@ __device__ __forceinline__ Rec block_arg(const Rec& v, RecSlot* slots, int& par)
   return warp_arg<PW>(t);
 }
 
-template <bool ONCHIP>
-__global__ void __launch_bounds__(NT, 1)
+template <class CFG, bool ONCHIP>
+__global__ void __launch_bounds__(CFG::NT, CFG::CTAS)
 k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil_all,
              const int32_t* __restrict__ node_cell_all, const int32_t* __restrict__ cell_node_all,
              const int32_t* __restrict__ n_nodes, const double* __restrict__ tau_all,
-             const int32_t* __restrict__ first_nan_cell, int X, int Y, int ldn, int latlon, int MA,
+             const int32_t* __restrict__ first_nan_cell, int B, int X, int Y, int ldn, int latlon, int MA,
              int32_t* __restrict__ area_cells_all, int32_t* __restrict__ area_start_all,
              int32_t* __restrict__ area_key_all, int32_t* __restrict__ n_areas_all,
              int32_t* __restrict__ label_all, int32_t* __restrict__ status_all,
-             unsigned char* __restrict__ scratch_all, size_t scratch_stride, int place_arg,
+             int* __restrict__ queue, unsigned char* __restrict__ scratch_all, size_t scratch_stride, int place_arg,
              unsigned long long* __restrict__ work_all) {
+  constexpr int NT = CFG::NT, NW = CFG::NW, NG = CFG::NG, FCAP = CFG::FCAP, BKW = CFG::BKW;
+  using IT = typename CFG::IT;
+  using FK = typename CFG::FK;
+  constexpr FK NOKEY = CFG::NOKEY;
   constexpr int MAXD = ONCHIP ? 6 : 16;        // pairwise tree depth: lists are <= C cells, C < 8192 when ONCHIP
   const int place = ONCHIP ? 0 : place_arg;   // ONCHIP: every array in shared memory (pointers known to be shared)
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -183,6 +209,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   __shared__ int sh_koff[MAXCH + 1], sh_uoff[MAXCH + 1];
   __shared__ int sh_goff[MAXCH + 1], sh_soff[MAXCH + 1], sh_xo[MAXCH], sh_r0[MAXCH], sh_so[MAXCH];
   __shared__ int sh_x[4];
+  __shared__ int sh_job;
   __shared__ unsigned long long sh_work;
   __shared__ unsigned long long ph[16];   // per-phase SM cycles (thread 0's view), reported through work[4..15]
   long long tick_last = 0;
@@ -198,8 +225,6 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
 #else
 #define TICK(i) do { } while (0)
 #endif
-  unsigned long long wk = 0;   // correlations consumed (algorithmic gathers)
-  unsigned long long bph[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // bookkeeping-warp phase cycles (its lane 0), work[16..23]
   long long btick = 0;
 #ifdef SIE_AREA_PHASE_TIMERS
 #define BTICK(i)                                                       \
@@ -212,31 +237,21 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
 #define BTICK(i) do { } while (0)
 #endif
 
-  const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = tid >> 3, j = tid & 7;
   const unsigned gmask = 0xffu << (lane & 24);
   const int C = X * Y;
-  const int N = min(n_nodes[b], ldn);
-  const double tau = tau_all[b];
-  const double* R = Rall + (size_t)b * ldn * ldn;
-  const double* sten = stencil_all + (size_t)b * ldn * 4;
-  const int32_t* cnode_g = cell_node_all + (size_t)b * C;
-  int32_t* out_cells = area_cells_all + (size_t)b * C;
-  int32_t* out_start = area_start_all + (size_t)b * (MA + 1);
-  int32_t* out_key = area_key_all + (size_t)b * MA;
-  int32_t* out_label = label_all + (size_t)b * C;
   int par = 0;
 
-  // ---- global scratch of this job
-  unsigned char* gp = scratch_all + (size_t)b * scratch_stride;
+  // ---- global scratch of this CTA (reused by every job it pops)
+  unsigned char* gp = scratch_all + (size_t)blockIdx.x * scratch_stride;
   auto gtake = [&](size_t bytes) { unsigned char* r = gp; gp += align_up(bytes, 256); return r; };
   int32_t* s1_cells = (int32_t*)gtake(sizeof(int32_t) * (size_t)C);   // step-1 member cells, area after area
-  int32_t* ibuf = (int32_t*)gtake(sizeof(int32_t) * (size_t)7 * C);
+  IT* ibuf = (IT*)gtake(sizeof(int32_t) * (size_t)7 * C);
   double* rowmean = (double*)gtake(sizeof(double) * rm_cap(C));
   const int dcap = d_cap(C);
   double* D = (double*)gtake(sizeof(double) * ((size_t)dcap * dcap + 128));
-  unsigned char* gtabs = gtake(area_tab_bytes(MA));
+  unsigned char* gtabs = gtake(area_tab_bytes(MA, sizeof(int32_t)));
   double* selfbuf = (double*)gtake(sizeof(double) * self_cap(C));
   // ---- shared memory: slot state | per-area tables | integer arrays (whatever `place` keeps on chip)
   unsigned char* sp = smem_raw;
@@ -247,28 +262,47 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   double* smean = (double*)stake(sizeof(double) * FCAP);       // its nanmean
   int32_t* snan = (int32_t*)stake(sizeof(int32_t) * FCAP);     // NaN entries seen
   int32_t* srow = (int32_t*)stake(sizeof(int32_t) * FCAP);     // node of the slot's cell, -1 = dead slot
-  AreaTabs S = carve_tabs((place & PL_AREA) ? gtabs : stake(area_tab_bytes(MA)), MA);
-  auto iarr = [&](int bit, int idx) -> int32_t* {
-    return (place & bit) ? ibuf + (size_t)idx * C : (int32_t*)stake(sizeof(int32_t) * (size_t)C);
+  AreaTabs<IT> S = carve_tabs<IT>((place & PL_AREA) ? gtabs : stake(area_tab_bytes(MA, sizeof(IT))), MA);
+  auto iarr = [&](int bit, int idx) -> IT* {
+    return (place & bit) ? ibuf + (size_t)idx * C : (IT*)stake(sizeof(IT) * (size_t)C);
   };
-  int32_t* lab = iarr(PL_LAB, 0);                      // [C] area key of each cell, -1 = unassigned
-  uint32_t* fkey = (uint32_t*)iarr(PL_FKEY, 1);        // [C] frontier key (step 1)
-  int32_t* flist = iarr(PL_FLIST, 2);                  // [C] frontier cell of each slot (step 1), -1 = dead
-  int32_t* hn = iarr(PL_HN, 3);                        // [C] node list of the current area (step 1) / best area (step 2)
-  int32_t* hc = iarr(PL_HC, 4);                        // [C] cell list of the best area (step 2)
-  int32_t* cnl = iarr(PL_CNL, 5);                      // [C] local copy of cell -> node
-  int32_t* knl = iarr(PL_KNL, 6);                      // [C] node lists of the neighbour areas (step 2)
-  const int32_t* cnode = cnl;
+  IT* lab = iarr(PL_LAB, 0);                           // [C] area key of each cell, -1 = unassigned
+  FK* fkey = (FK*)iarr(PL_FKEY, 1);                    // [C] frontier key (step 1)
+  IT* flist = iarr(PL_FLIST, 2);                       // [C] frontier cell of each slot (step 1), -1 = dead
+  IT* hn = iarr(PL_HN, 3);                             // [C] node list of the current area (step 1) / best area (step 2)
+  IT* hc = iarr(PL_HC, 4);                             // [C] cell list of the best area (step 2)
+  IT* cnl = iarr(PL_CNL, 5);                           // [C] local copy of cell -> node
+  IT* knl = iarr(PL_KNL, 6);                           // [C] node lists of the neighbour areas (step 2)
+  const IT* cnode = cnl;
 
-  for (int c = tid; c < C; c += NT) { lab[c] = -1; fkey[c] = NOKEY; out_label[c] = -1; cnl[c] = cnode_g[c]; }
+  // =============================================================== persistent loop over the job queue
+  for (;;) {
+  __syncthreads();                        // the previous job's state is no longer read
+  if (tid == 0) sh_job = atomicAdd(queue, 1);
+  __syncthreads();
+  const int b = sh_job;
+  if (b >= B) break;
+  unsigned long long wk = 0;   // correlations consumed (algorithmic gathers)
+  unsigned long long bph[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // bookkeeping-warp phase cycles (its lane 0), work[16..23]
+  const int N = min(n_nodes[b], ldn);
+  const double tau = tau_all[b];
+  const double* R = Rall + (size_t)b * ldn * ldn;
+  const double* sten = stencil_all + (size_t)b * ldn * 4;
+  const int32_t* cnode_g = cell_node_all + (size_t)b * C;
+  int32_t* out_cells = area_cells_all + (size_t)b * C;
+  int32_t* out_start = area_start_all + (size_t)b * (MA + 1);
+  int32_t* out_key = area_key_all + (size_t)b * MA;
+  int32_t* out_label = label_all + (size_t)b * C;
+
+  for (int c = tid; c < C; c += NT) { lab[c] = -1; fkey[c] = NOKEY; out_label[c] = -1; cnl[c] = (IT)cnode_g[c]; }
   if (tid < 16) ph[tid] = 0ull;
   if (tid == 0) { n_areas_all[b] = 0; out_start[0] = 0; sh_work = 0ull; if (work_all) work_all[SIE_AREA_WORK * b] = 0ull; }
   __syncthreads();
   if (first_nan_cell[b] < 0) {            // :50-51 IndexError in the reference
     if (tid == 0) status_all[b] = SIE_JOB_NO_NAN_CELL;
-    return;
+    continue;
   }
-  if (status_all[b] == SIE_JOB_CAPACITY) return;   // K1 already flagged this job
+  if (status_all[b] == SIE_JOB_CAPACITY) continue;   // K1 already flagged this job
 
   // ---- step-1 helpers (bookkeeping warp only) -----------------------------------------------------------
   // State of slot s (frontier cell with node `fnode` vs the first n <= 128 member nodes hn[0..n)) by one 8-lane
@@ -317,8 +351,8 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         if (lab[f] >= 0 || fn < 0 || fn >= N) f = -1;
       }
       if (f >= 0) {
-        const uint32_t key = ((uint32_t)d << 28) | (uint32_t)p;
-        const uint32_t old = fkey[f];
+        const FK key = (FK)(((uint32_t)d << CFG::DSHIFT) | (uint32_t)p);
+        const FK old = fkey[f];
         isnew = (old == NOKEY);
         if (key < old) fkey[f] = key;
       }
@@ -330,7 +364,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
     if (isnew) {
       const int r = __popc(mnew & ((1u << lane) - 1u));
       myslot = (hole >= 0) ? (r == 0 ? hole : nf + r - 1) : nf + r;
-      flist[myslot] = f;
+      flist[myslot] = (IT)f;
     }
     const int nf_new = nf + cntnew - ((hole >= 0 && cntnew > 0) ? 1 : 0);
     if (hole >= 0 && cntnew == 0 && lane == 0) { flist[hole] = -1; if (hole < FCAP) srow[hole] = -1; }
@@ -385,7 +419,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
     }
     Rec cand = rec_none();
     if (dir >= 0) { cand.ord = 1ull; cand.pri = (unsigned long long)(~(uint32_t)c) << 32; cand.a = (uint32_t)c; cand.b = (uint32_t)dir; }
-    const Rec sw = block_arg<1>(cand, rslots, par);   // earliest cell wins
+    const Rec sw = block_arg<1, NW>(cand, rslots, par);   // earliest cell wins
     TICK(0);                              // seed search
     if (sw.ord == 0ull) { c0 += NT; continue; }
     const int seed = (int)sw.a;
@@ -407,7 +441,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
     __syncthreads();                      // every thread has read lab[nbr] before it changes
     if (warp == BKW) {
       if (lane == 0) {
-        lab[seed] = k; lab[nbr] = k;
+        lab[seed] = (IT)k; lab[nbr] = (IT)k;
         hn[0] = cnode[seed]; hn[1] = cnode[nbr];
         s1_cells[base] = seed; s1_cells[base + 1] = nbr;
       }
@@ -429,7 +463,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         if (tid < nf) cell = flist[tid];
         if (cell >= 0) {
           const double mean = smean[tid];
-          if (mean == mean) { loc.ord = ord_of(mean); loc.pri = (unsigned long long)(~fkey[cell]) << 32; loc.a = (uint32_t)tid; loc.b = (uint32_t)cell; }
+          if (mean == mean) { loc.ord = ord_of(mean); loc.pri = (unsigned long long)(~(uint32_t)fkey[cell]) << 32; loc.a = (uint32_t)tid; loc.b = (uint32_t)cell; }
         }
         const unsigned live = __ballot_sync(FULL, cell >= 0);
         if (lane == 0) wk += (unsigned long long)n * (unsigned long long)__popc(live);
@@ -447,13 +481,13 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
           nanc += __shfl_xor_sync(gmask, nanc, 4);
           const double mean = sum / (double)(n - nanc);   // np.nanmean: NaN -> 0, divide by the non-NaN count
           if (mean == mean) {
-            Rec cur; cur.ord = ord_of(mean); cur.pri = (unsigned long long)(~fkey[f]) << 32; cur.a = (uint32_t)q; cur.b = (uint32_t)f;
+            Rec cur; cur.ord = ord_of(mean); cur.pri = (unsigned long long)(~(uint32_t)fkey[f]) << 32; cur.a = (uint32_t)q; cur.b = (uint32_t)f;
             loc = rec_max(loc, cur);
           }
         }
       }
       TICK(10);                           // evaluate
-      const Rec win = block_arg<1>(loc, rslots, par);
+      const Rec win = block_arg<1, NW>(loc, rslots, par);
       TICK(1);                            // argmax
       if (win.ord == 0ull || !(ord_to_double(win.ord) > tau)) break;   // :134 (nanmax of all-NaN is NaN -> stop)
       const int widx = (int)win.a;
@@ -471,8 +505,8 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
       if (warp == BKW) {
         BTICK(0);                         // everything outside the update (evaluate, argmax, waiting)
         if (lane == 0) {
-          lab[m] = k;
-          hn[n] = mnode;
+          lab[m] = (IT)k;
+          hn[n] = (IT)mnode;
           s1_cells[base + n] = m;
           fkey[m] = NOKEY;
         }
@@ -520,7 +554,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
     __syncthreads();
     for (int q = tid; q < nf; q += NT) { const int f = flist[q]; if (f >= 0) fkey[f] = NOKEY; }
     if (tid == 0) {
-      S.a_start[k] = base; S.a_len[k] = n; S.seg_next[k] = -1; S.tail[k] = k; S.size[k] = n; S.fin[k] = 0;
+      S.a_start[k] = (IT)base; S.a_len[k] = (IT)n; S.seg_next[k] = -1; S.tail[k] = (IT)k; S.size[k] = (IT)n; S.fin[k] = 0;
       S.okey[k] = NOKEY64;
       S.xep[k] = 0; S.self_sz[k] = 0;
     }
@@ -530,7 +564,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   }
   if (overflow) {
     if (tid == 0) status_all[b] = SIE_JOB_CAPACITY;
-    return;
+    continue;
   }
 
   // =============================================================== step 2 (:200-265)
@@ -581,7 +615,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         loc = rec_max(loc, cur);
       }
     }
-    const Rec bw = block_arg<1>(loc, rslots, par);
+    const Rec bw = block_arg<1, NW>(loc, rslots, par);
     if (bw.ord <= 1ull) break;   // no areas at all (:212) or all finalised
     const int best = (int)bw.a;
     ++n_rounds;
@@ -589,7 +623,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
       int off = 0;
       for (int s = best; s >= 0; s = S.seg_next[s]) {
         const int st = S.a_start[s], ln = S.a_len[s];
-        for (int i = tid; i < ln; i += NT) { const int c = s1_cells[st + i]; hc[off + i] = c; hn[off + i] = cnode[c]; }
+        for (int i = tid; i < ln; i += NT) { const int c = s1_cells[st + i]; hc[off + i] = (IT)c; hn[off + i] = cnode[c]; }
         off += ln;
       }
       nb = off;
@@ -618,7 +652,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         if (!wrapped && S.fin[kk]) continue;          // finalised cells are `unavail` (sentinel), :54-77
         const unsigned long long key = ((unsigned long long)p << 32) | ((unsigned long long)kk << 2) | (unsigned)d;
         const unsigned long long old = atomicMin(&S.okey[kk], key);
-        if (old == NOKEY64) S.nlist[atomicAdd(&sh_i[3], 1)] = kk;
+        if (old == NOKEY64) S.nlist[atomicAdd(&sh_i[3], 1)] = (IT)kk;
       }
     }
     __syncthreads();
@@ -631,11 +665,11 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         const int kk = S.nlist[q], nk = S.size[kk];
         if (S.xep[kk] != epoch) {
           if (top - nk < nb) { ok = 0; break; }
-          top -= nk; S.xoff[kk] = top; S.xep[kk] = epoch; S.xrows[kk] = 0;
+          top -= nk; S.xoff[kk] = (IT)top; S.xep[kk] = (IT)epoch; S.xrows[kk] = 0;
         }
         if (S.self_sz[kk] != nk && S.self_sz[kk] != -nk) {
           if ((size_t)stop + nk > self_cap(C)) { ok = 0; break; }
-          S.self_off[kk] = stop; stop += nk; S.self_sz[kk] = -nk;     // allocated, not yet computed
+          S.self_off[kk] = (IT)stop; stop += nk; S.self_sz[kk] = (IT)-nk;     // allocated, not yet computed
         }
       }
       sh_x[0] = top; sh_x[1] = ok; sh_x[2] = stop;
@@ -672,7 +706,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
             sh_xo[c] = S.xoff[kk]; sh_r0[c] = S.xrows[kk]; sh_so[c] = S.self_off[kk];
             go += nb - S.xrows[kk];
             if (S.self_sz[kk] != sz) so += sz;
-            S.xrows[kk] = nb;
+            S.xrows[kk] = (IT)nb;
           }
         }
         sh_koff[nch] = off; sh_uoff[nch] = uo; sh_goff[nch] = go; sh_soff[nch] = so;
@@ -698,7 +732,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
           while (u >= sh_goff[qc + 1]) ++qc;
           const int p = sh_r0[qc] + (u - sh_goff[qc]);
           const int nk = sh_koff[qc + 1] - sh_koff[qc];
-          const int32_t* kn = knl + sh_koff[qc];
+          const IT* kn = knl + sh_koff[qc];
           const double* row = R + (size_t)hn[p] * ldn;
           double* dst = D + (size_t)p * ld + sh_xo[qc];
           for (int qq = 0; qq < nk; qq += 64) {
@@ -718,13 +752,13 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
           while (u >= sh_soff[qc + 1]) ++qc;
           const int pp = u - sh_soff[qc];
           const int nk = sh_koff[qc + 1] - sh_koff[qc];
-          const int32_t* kn = knl + sh_koff[qc];
+          const IT* kn = knl + sh_koff[qc];
           const int len = nk - 1 - pp;
           int nanc = 0;
           double sum = 0.0;
           if (len > 0) {
             const double* row = R + (size_t)kn[pp] * ldn;
-            const int32_t* kq = kn + pp + 1;
+            const IT* kq = kn + pp + 1;
             sum = sie_pw_sum8<MAXD>([&](int i) { return __ldg(row + kq[i]); }, len, j, gmask, nanc);
             nanc += __shfl_xor_sync(gmask, nanc, 1);
             nanc += __shfl_xor_sync(gmask, nanc, 2);
@@ -786,7 +820,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
           const int p = u - sh_uoff[qc];
           const int nk = sh_koff[qc + 1] - sh_koff[qc];
           const int n = nb + nk;
-          const int32_t* kn = knl + sh_koff[qc];
+          const IT* kn = knl + sh_koff[qc];
           const int len = n - 1 - p;
           int nanc = 0;
           double sum = 0.0;
@@ -794,10 +828,10 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
             if (p < nb) {
               const double* row = R + (size_t)hn[p] * ldn;
               const int nbb = nb - 1 - p;              // elements of the row inside the best area
-              sum = sie_pw_sum8<MAXD>([&](int i) { const int32_t* q = (i < nbb) ? hn + (p + 1 + i) : kn + max(i - nbb, 0); return __ldg(row + *q); }, len, j, gmask, nanc);
+              sum = sie_pw_sum8<MAXD>([&](int i) { const IT* q = (i < nbb) ? hn + (p + 1 + i) : kn + max(i - nbb, 0); return __ldg(row + *q); }, len, j, gmask, nanc);
             } else {
               const double* row = R + (size_t)kn[p - nb] * ldn;
-              const int32_t* kq = kn + (p - nb) + 1;
+              const IT* kq = kn + (p - nb) + 1;
               sum = sie_pw_sum8<MAXD>([&](int i) { return __ldg(row + kq[i]); }, len, j, gmask, nanc);
             }
             nanc += __shfl_xor_sync(gmask, nanc, 1);
@@ -838,8 +872,8 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         loc2 = rec_max(loc2, cur);
       }
     }
-    const Rec firstn = block_arg<2>(f1, rslots, par);
-    const Rec win = block_arg<2>(loc2, rslots, par);
+    const Rec firstn = block_arg<2, NW>(f1, rslots, par);
+    const Rec win = block_arg<2, NW>(loc2, rslots, par);
     bool merge = false;
     int kk = -1;
     if (nn > 0 && win.ord != 0ull) {
@@ -856,15 +890,15 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         const int st = S.a_start[s], ln = S.a_len[s];
         for (int i = tid; i < ln; i += NT) {
           const int c = s1_cells[st + i];
-          hc[off + i] = c; hn[off + i] = cnode[c]; lab[c] = best;
+          hc[off + i] = (IT)c; hn[off + i] = cnode[c]; lab[c] = (IT)best;
         }
         off += ln;
       }
       __syncthreads();
       if (tid == 0) {
-        S.seg_next[S.tail[best]] = kk;
+        S.seg_next[S.tail[best]] = (IT)kk;
         S.tail[best] = S.tail[kk];
-        S.size[best] += S.size[kk];
+        S.size[best] = (IT)(S.size[best] + S.size[kk]);
         S.size[kk] = 0;
       }
       if (off > xtop) { ++epoch; xtop = ld; }  // the best columns would run into the cross blocks: drop them
@@ -899,7 +933,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
       if (S.size[k] > 0) {
         out_key[cnt] = k;
         out_start[cnt] = off;
-        S.nlist[cnt] = k;
+        S.nlist[cnt] = (IT)k;
         off += S.size[k];
         ++cnt;
       }
@@ -923,13 +957,63 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
       off += ln;
     }
   }
+  }   // persistent loop over the job queue
+}
+
+template <class CFG, bool ONCHIP>
+int launch_area(const SieDevice* dev, int slot, int grid, size_t smem, cudaStream_t st, const double* R,
+                const double* stencil, const int32_t* node_cell, const int32_t* cell_node, const int32_t* n_nodes,
+                const double* tau, const int32_t* first_nan_cell, int B, int X, int Y, int ldn, int latlon,
+                int max_areas, int32_t* area_cells, int32_t* area_start, int32_t* area_key, int32_t* n_areas,
+                int32_t* label, int32_t* status, int* queue, unsigned char* scratch, size_t per_cta, int place,
+                unsigned long long* work) {
+  auto kern = k_area_level<CFG, ONCHIP>;
+  if (int rc = sie_ensure_smem(dev, slot, (const void*)kern, smem)) return rc;
+  kern<<<grid, CFG::NT, smem, st>>>(R, stencil, node_cell, cell_node, n_nodes, tau, first_nan_cell, B, X, Y, ldn, latlon,
+                                    max_areas, area_cells, area_start, area_key, n_areas, label, status, queue, scratch,
+                                    per_cta, place, work);
+  return SIE_OK;
+}
+
+// persistent grid: CTAs per SM of the variant this (grid, capacity) selects, and its dynamic shared memory
+struct AreaPlan { int variant, ctas_per_sm, place; size_t smem; };   // variant 0: <256,i16>, 1: <512,i16>, 2: <512,i32>
+AreaPlan plan_area(const SieDevice* dev, int B, int C, int ldn, int max_areas) {
+  AreaPlan pl = {2, 1, 0, 0};
+  const size_t budget = (size_t)dev->max_smem_optin - 4096;    // static shared memory + alignment slack
+  if (C < 8192 && ldn <= 32767 && max_areas <= 32766) {
+    const size_t i16 = 7 * align_up(sizeof(int16_t) * (size_t)C, 16) + area_tab_bytes(max_areas, sizeof(int16_t)) + 64;
+    const size_t s256 = align_up(slot_bytes(AreaCfg<256, int16_t>::FCAP), 16) + i16;
+    const size_t s512 = align_up(slot_bytes(AreaCfg<512, int16_t>::FCAP), 16) + i16;
+    // two 256-thread CTAs per SM give ~1.2x the throughput of one 512-thread CTA (a job alone takes 1.3x longer, paired
+    // 1.6x: tools/prof_area.py) -- but only when there are enough jobs to pair them on every SM
+    if (B > 2 * dev->sm_count && 2 * (s256 + 4096 + 1024) <= (size_t)dev->smem_per_sm) {
+      pl.variant = 0; pl.ctas_per_sm = 2; pl.smem = s256; return pl;
+    }
+    if (s512 <= budget) { pl.variant = 1; pl.smem = s512; return pl; }
+  }
+  // 32-bit indices.  Shared-memory placement: slot state always on chip; then evict arrays to global scratch, least
+  // latency-critical first, until the rest fits.
+  const size_t ibytes = align_up(sizeof(int32_t) * (size_t)C, 16);
+  const size_t tabs = area_tab_bytes(max_areas, sizeof(int32_t));
+  size_t smem = align_up(slot_bytes(AreaCfg<512, int32_t>::FCAP), 16) + 64 + tabs + 7 * ibytes;
+  const int order[8] = {PL_KNL, PL_AREA, PL_HC, PL_FLIST, PL_HN, PL_FKEY, PL_CNL, PL_LAB};
+  for (int i = 0; i < 8 && smem > budget; ++i) {
+    pl.place |= order[i];
+    smem -= (order[i] == PL_AREA) ? tabs : ibytes;
+  }
+  pl.smem = smem;
+  return pl;
 }
 
 }  // namespace
 
 extern "C" size_t sie_area_level_scratch_bytes(int B, int C) {
-  // per-area arrays are sized for the worst case max_areas = C/2 + 1
-  return (size_t)B * scratch_per_job(C, C / 2 + 1);
+  // one scratch block per CTA of the persistent grid (at most two CTAs per SM), not per job; per-area arrays are sized
+  // for the worst case max_areas = C/2 + 1
+  const SieDevice* dev = sie_device();
+  const int sms = (dev && dev->sm_count > 0) ? dev->sm_count : 148;
+  const int g = B < 2 * sms ? (B > 0 ? B : 1) : 2 * sms;
+  return QUEUE_BYTES + (size_t)g * scratch_per_cta(C, C / 2 + 1);
 }
 
 extern "C" int sie_area_level(const double* R, const double* stencil, const int32_t* node_cell,
@@ -944,29 +1028,34 @@ extern "C" int sie_area_level(const double* R, const double* stencil, const int3
   const int C = X * Y;
   SIE_CHECK_ARG(max_areas <= C / 2 + 1, "max_areas cannot exceed C/2+1");
   SIE_CHECK_ARG((long long)C < (1ll << 22), "grid too large (frontier key encoding / pairwise tree depth)");
-  const size_t per_job = scratch_per_job(C, max_areas);
-  SIE_CHECK_ARG(scratch_bytes >= per_job * (size_t)B, "scratch too small");
-  int dev = 0, max_optin = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  // Shared-memory placement: slot state always on chip; then evict arrays to global scratch, least
-  // latency-critical first, until the rest fits.
-  const size_t budget = (size_t)max_optin - 4096;    // static shared memory + alignment slack
-  const size_t ibytes = align_up(sizeof(int32_t) * (size_t)C, 16);
-  size_t smem = align_up(slot_bytes(), 16) + 64 + area_tab_bytes(max_areas) + 7 * ibytes;
-  int place = 0;
-  const int order[8] = {PL_KNL, PL_AREA, PL_HC, PL_FLIST, PL_HN, PL_FKEY, PL_CNL, PL_LAB};
-  for (int i = 0; i < 8 && smem > budget; ++i) {
-    place |= order[i];
-    smem -= (order[i] == PL_AREA) ? area_tab_bytes(max_areas) : ibytes;
-  }
-  SIE_CHECK_ARG(smem <= budget, "shared memory budget");
-  auto kern = (place == 0 && C < 8192) ? k_area_level<true> : k_area_level<false>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kern<<<B, NT, smem, (cudaStream_t)stream>>>(
-      R, stencil, node_cell, cell_node, n_nodes, tau, first_nan_cell, X, Y, ldn, latlon, max_areas, area_cells,
-      area_start, area_key, n_areas, label, status, (unsigned char*)scratch, per_job, place,
-      (unsigned long long*)work);
+  const SieDevice* dev = sie_device();
+  if (!dev) return SIE_ERR_LAUNCH;
+  const AreaPlan pl = plan_area(dev, B, C, ldn, max_areas);
+  SIE_CHECK_ARG(pl.smem <= (size_t)dev->max_smem_optin - 4096, "shared memory budget");
+  const size_t per_cta = scratch_per_cta(C, max_areas);
+  SIE_CHECK_ARG(scratch_bytes >= QUEUE_BYTES + per_cta, "scratch too small");
+  long long grid = (long long)pl.ctas_per_sm * dev->sm_count;
+  if (grid > B) grid = B;
+  const long long fit = (long long)((scratch_bytes - QUEUE_BYTES) / per_cta);
+  if (grid > fit) grid = fit;
+  cudaStream_t st = (cudaStream_t)stream;
+  int* queue = reinterpret_cast<int*>(scratch);
+  unsigned char* blocks = reinterpret_cast<unsigned char*>(scratch) + QUEUE_BYTES;
+  if (cudaMemsetAsync(queue, 0, sizeof(int), st) != cudaSuccess) SIE_CHECK_LAUNCH();
+  int rc;
+#define SIE_AREA_ARGS                                                                                                   \
+  R, stencil, node_cell, cell_node, n_nodes, tau, first_nan_cell, B, X, Y, ldn, latlon, max_areas, area_cells, area_start, \
+      area_key, n_areas, label, status, queue, blocks, per_cta, pl.place, (unsigned long long*)work
+  if (pl.variant == 0)
+    rc = launch_area<AreaCfg<256, int16_t>, true>(dev, SIE_K_AREA_ON16_2, (int)grid, pl.smem, st, SIE_AREA_ARGS);
+  else if (pl.variant == 1)
+    rc = launch_area<AreaCfg<512, int16_t>, true>(dev, SIE_K_AREA_ON16, (int)grid, pl.smem, st, SIE_AREA_ARGS);
+  else if (pl.place == 0 && C < 8192)
+    rc = launch_area<AreaCfg<512, int32_t>, true>(dev, SIE_K_AREA_ON32, (int)grid, pl.smem, st, SIE_AREA_ARGS);
+  else
+    rc = launch_area<AreaCfg<512, int32_t>, false>(dev, SIE_K_AREA_OFF32, (int)grid, pl.smem, st, SIE_AREA_ARGS);
+#undef SIE_AREA_ARGS
+  if (rc) return rc;
   SIE_CHECK_LAUNCH();
   return SIE_OK;
 }

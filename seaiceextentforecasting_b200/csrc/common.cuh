@@ -7,6 +7,20 @@
 
 void sie_set_error(const char* fmt, ...);
 
+// Cached facts of one device + the dynamic-shared-memory limit each kernel was last given there (abi.cu).
+#define SIE_MAX_DEVICES 64
+#define SIE_ATTR_SLOTS 16
+enum SieAttrSlot { SIE_K_DETREND = 0, SIE_K_CORR_TILES, SIE_K_CORR_ROWS_ST, SIE_K_CORR_ROWS_TAU, SIE_K_AREA_ON32,
+                   SIE_K_AREA_OFF32, SIE_K_AREA_ON16, SIE_K_AREA_ON16_2, SIE_K_GP, SIE_K_LINKS };
+struct SieDevice {
+  volatile int ready;
+  int ordinal, sm_count, max_smem_optin, smem_per_sm;
+  size_t l2_bytes;
+  long long attr_smem[SIE_ATTR_SLOTS];
+};
+const SieDevice* sie_device(void);                     // current device, nullptr (error set) if there is none
+int sie_ensure_smem(const SieDevice* d, int slot, const void* func, size_t bytes);
+
 #define SIE_CHECK_ARG(cond, msg)                 \
   do {                                           \
     if (!(cond)) {                               \

@@ -366,6 +366,7 @@ constexpr int RW_D_LD = TILE_N + 8;              // 72 doubles = 576 B per stage
 constexpr int RW_T_LD = TILE + 2;                // 130 doubles = 1040 B per staged transposed row
 template <bool STORE> constexpr int rw_threads() { return (RW_CWARPS + 1 + (STORE ? RW_SWARPS : 0)) * 32; }
 
+constexpr long long kOneBits = 0x3ff0000000000000LL;   // int64 image of 1.0: after clip_unit only NaNs lie above it
 // clip to [-1, 1] (np.clip keeps NaN): one integer compare on the high word in the common |v| < 1 case
 __device__ __forceinline__ double clip_unit(double v) {
   const unsigned hi = (unsigned)__double2hiint(v) & 0x7fffffffu;
@@ -550,7 +551,8 @@ k_corr_rows(const double* __restrict__ z, const long long* __restrict__ prefix, 
         for (int j = 0; j < 2; ++j) {
           const int lj = wc * 16 + j * 8 + 2 * (lane & 3);
           const double v0 = acc[i][j][0], v1 = acc[i][j][1];
-          const bool t0 = __double_as_longlong(v0) > rcb, t1 = __double_as_longlong(v1) > rcb;
+          const long long i0 = __double_as_longlong(v0), i1 = __double_as_longlong(v1);
+          const bool t0 = i0 > rcb && i0 <= kOneBits, t1 = i1 > rcb && i1 <= kOneBits;   // NaN images lie above 1.0's
           lsum += t0 ? v0 : 0.0;                                   // adding +0.0 leaves a non-negative sum unchanged
           lsum += t1 ? v1 : 0.0;
           lcnt += (int)t0 + (int)t1;
@@ -572,7 +574,8 @@ k_corr_rows(const double* __restrict__ z, const long long* __restrict__ prefix, 
           for (int h = 0; h < 2; ++h) {
             const double v = acc[i][j][h];
             const bool up = gi < N && gj + h < N && (dk >= 2 || gj + h > gi);   // strictly above the diagonal
-            const bool t = up && __double_as_longlong(v) > rcb;
+            const long long iv = __double_as_longlong(v);
+            const bool t = up && iv > rcb && iv <= kOneBits;
             lsum += t ? v : 0.0;
             lcnt += (int)t;
             if (STORE) {
@@ -699,7 +702,8 @@ extern "C" size_t sie_corr_tau_scratch_bytes(int B, int ldn) {
 extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32_t* job_T,
                             const double* r_crit, int B, int ldn, int Tp, double* R, double* tile_part,
                             size_t tile_part_bytes, double* tau_sum, int64_t* tau_cnt, double* tau,
-                            int shard_rank, int shard_count, void* stream) {
+                            int shard_rank, int shard_count, int kernel, void* stream) {
+  SIE_CHECK_ARG(kernel == SIE_CORR_AUTO || kernel == SIE_CORR_TILES || kernel == SIE_CORR_ROWS, "unknown kernel choice");
   SIE_CHECK_ARG(z && n_nodes && job_T && r_crit && tile_part && tau_sum && tau_cnt && tau, "null pointer");
   SIE_CHECK_ARG(B > 0 && ldn > 0 && (ldn % TILE) == 0, "ldn must be a positive multiple of 128");
   SIE_CHECK_ARG(Tp >= 4 && (Tp % 4) == 0, "Tp must be a multiple of 4");
@@ -709,10 +713,9 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
   const size_t smem_panels = (size_t)(TILE + TILE_N) * Tp * sizeof(double);
   const size_t smem_stage = R ? (size_t)TILE * CS_LD * sizeof(double) : 0;   // output tile staged over the panels
   const size_t smem = smem_panels > smem_stage ? smem_panels : smem_stage;
-  int dev = 0, sms = 0, max_optin = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const SieDevice* dev = sie_device();
+  if (!dev) return SIE_ERR_LAUNCH;
+  const int sms = dev->sm_count, max_optin = dev->max_smem_optin;
   // scratch layout: [prefix (B+1) int64][pad to 256][warp partials 16 pairs/tile][pad][item table 32 B/tile][pad][tile pairs]
   long long* prefix = reinterpret_cast<long long*>(tile_part);
   unsigned char* base = reinterpret_cast<unsigned char*>(tile_part);
@@ -738,18 +741,17 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
   if (S > RW_MAXS) S = RW_MAXS;
   // default: rows kernel for the tau-only pass (25.2 vs 22.6 TFLOP/s at 25 km), tile kernel when R is stored (2.14 vs
   // 2.29 ms on the 144-network sweep: the staged tile's extra trip through the LSU pipe costs what the resident A
-  // panel saves).  SIE_CORR_KERNEL=tiles|rows overrides (A/B timing, parity tests of both paths).
-  const char* force = getenv("SIE_CORR_KERNEL");
-  const bool want_rows = force ? force[0] == 'r' : (R == nullptr);
+  // panel saves).  `kernel` = SIE_CORR_TILES / SIE_CORR_ROWS overrides (A/B timing, parity tests of both paths).
+  const bool want_rows = kernel == SIE_CORR_AUTO ? (R == nullptr) : (kernel == SIE_CORR_ROWS);
   const bool use_rows = S >= 2 && want_rows;
   if (use_rows) {
     const size_t rsmem = rw_fixed + (size_t)S * rw_stage;
     const int grid = (int)(max_items < sms ? max_items : sms);
     if (R) {
-      cudaFuncSetAttribute(k_corr_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      if (int rc = sie_ensure_smem(dev, SIE_K_CORR_ROWS_ST, (const void*)k_corr_rows<true>, rsmem)) return rc;
       k_corr_rows<true><<<grid, rw_threads<true>(), rsmem, st>>>(z, prefix, table, B, ldn, Tp, S, R, parts);
     } else {
-      cudaFuncSetAttribute(k_corr_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      if (int rc = sie_ensure_smem(dev, SIE_K_CORR_ROWS_TAU, (const void*)k_corr_rows<false>, rsmem)) return rc;
       k_corr_rows<false><<<grid, rw_threads<false>(), rsmem, st>>>(z, prefix, table, B, ldn, Tp, S, R, parts);
     }
     SIE_CHECK_LAUNCH();
@@ -760,7 +762,7 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
       sie_set_error("sie_corr_tau: Tp=%d needs %zu B of shared memory (> %d)", Tp, smem, max_optin);
       return SIE_ERR_UNSUPPORTED;
     }
-    cudaFuncSetAttribute(k_corr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (int rc = sie_ensure_smem(dev, SIE_K_CORR_TILES, (const void*)k_corr_tiles, smem)) return rc;
     const long long slots = (long long)CTAS_PER_SM * sms;
     int grid = (int)(max_items < slots ? max_items : slots);
     k_corr_tiles<<<grid, NTHREADS, smem, st>>>(z, n_nodes, job_T, r_crit, prefix, table, B, ldn, Tp, R, tile_pair);

@@ -229,7 +229,9 @@ extern "C" int sie_detrend_zscore(const double* fields, const int32_t* job_field
   const int ld = Tp | 1;                                     // odd row stride (doubles) >= Tp >= Tstride
   const size_t smem = sizeof(double) * (size_t)DT_CELLS * ld;
   SIE_CHECK_ARG(smem <= 200 * 1024, "window too long for the shared-memory staging");
-  cudaFuncSetAttribute(k_detrend_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const SieDevice* dev = sie_device();
+  if (!dev) return SIE_ERR_LAUNCH;
+  if (int rc = sie_ensure_smem(dev, SIE_K_DETREND, (const void*)k_detrend_cells, smem)) return rc;
   k_detrend_cells<<<dim3((unsigned)((C + DT_CELLS - 1) / DT_CELLS), (unsigned)B), DT_CELLS, smem, st>>>(
       fields, job_field, job_T, C, Tstride, ld, do_detrend, dt, trend, cell_node, first_nan_cell);
   SIE_CHECK_LAUNCH();

@@ -573,7 +573,9 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
         double xn = 0.0, dot = 0.0;
         for (int t = 0; t < n; ++t) { const double d = x[t] - xm; xn = fma(d, d, xn); dot = fma(d, sm.y[t] - ymean, dot); }
         double r = dot / (sqrt(xn) * ynorm);
-        r = fmax(-1.0, fmin(1.0, r));
+        // pearsonr clips to [-1, 1]; a constant series gives NaN, which must stay NaN (fmin/fmax would return the
+        // non-NaN operand): `r > 0` / `r < 0` then reject it like the reference does
+        if (r == r) r = fmax(-1.0, fmin(1.0, r));
         if (sst) flag = (r < 0.0) ? 2 : 0;
         else if (pr.rule == 1) flag = 1;
         else if (pr.rule == 0) flag = (r > 0.0) ? 1 : 0;
@@ -596,8 +598,10 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
     }
     const int np_ = sm.misc[0];
     res.n_pred = np_;
-    if (np_ == 0 || np_ > ld) {
-      if (tid == 0) { res.info = (np_ == 0) ? -1 : -2; for (int k = 0; k < ns; ++k) out[(size_t)p * ns + k] = res; }
+    // fewer than two predictors: the reference's forecast() raises (no column: IndexError at `X[-1,:]`; one column:
+    // np.cov is 0-d and np.fill_diagonal raises ValueError, north/June1st.py:228-232)
+    if (np_ < 2 || np_ > ld) {
+      if (tid == 0) { res.info = (np_ < 2) ? -1 : -2; for (int k = 0; k < ns; ++k) out[(size_t)p * ns + k] = res; }
       continue;
     }
     // ---- X (n+1 rows) with optional column z-score over all n+1 rows (:226-227)
@@ -821,13 +825,8 @@ __host__ size_t gp_per_cta_bytes(int max_pred) {
 }
 __host__ size_t gp_header_bytes(int P) { return ((size_t)256 + (size_t)P * sizeof(int32_t) + 255) / 256 * 256; }
 int gp_grid(int P) {
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) {
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
-  } else {
-    (void)cudaGetLastError();
-  }
+  const SieDevice* dev = sie_device();
+  const int sms = (dev && dev->sm_count > 0) ? dev->sm_count : 148;
   const int g = 2 * sms;     // shared memory (~106 KB) and 128 registers/thread allow two CTAs per SM
   return P < g ? P : g;
 }
@@ -859,7 +858,9 @@ static int gp_launch(const SieGpProblem* prob, int P, const double* y_all, const
   k_gp_order<<<1, 1024, 0, st>>>(prob, P, n_areas_sic, n_areas_sst, order, queue);
   SIE_CHECK_LAUNCH();
   const size_t smem = sizeof(Smem);
-  cudaFuncSetAttribute(k_gp_forecast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const SieDevice* dev = sie_device();
+  if (!dev) return SIE_ERR_LAUNCH;
+  if (int rc = sie_ensure_smem(dev, SIE_K_GP, (const void*)k_gp_forecast, smem)) return rc;
   k_gp_forecast<<<grid, GT, smem, st>>>(prob, P, y_all, anom_sic, n_areas_sic, max_areas_sic, Tstride_sic, anom_sst,
                                         n_areas_sst, max_areas_sst, Tstride_sst, max_pred, out,
                                         (unsigned char*)scratch + head, per, order, queue, sig_grid, n_sig);

@@ -80,7 +80,9 @@ class NetworkBatch:
         self.Tp = pad_T(self.Tstride)
         n_upper = self.C if n_upper is None else int(n_upper)
         self.ldn = max(128, (n_upper + 127) // 128 * 128)
-        self.MA = int(max_areas) if max_areas else min(self.C // 2 + 1, 1024)
+        # area capacity (step-1 areas per network).  768 keeps the per-area tables of the 57x57 / 26x90 grids small enough
+        # for two domain-growth CTAs per SM (csrc/area.cu plan_area); a job that needs more reports SIE_JOB_CAPACITY
+        self.MA = int(max_areas) if max_areas else min(self.C // 2 + 1, 768)
         dev = "cuda"
         f64, i32 = torch.float64, torch.int32
         B_, C_, ldn, MA, Ts, Tp = self.B, self.C, self.ldn, self.MA, self.Tstride, self.Tp
@@ -105,8 +107,7 @@ class NetworkBatch:
         self.area_key = torch.empty((B_, MA), dtype=i32, device=dev)
         self.n_areas = torch.zeros((B_,), dtype=i32, device=dev)
         self.label = torch.empty((B_, C_), dtype=i32, device=dev)
-        self.area_scratch_bytes = int(self.lib.sie_area_level_scratch_bytes(B_, C_))
-        self.area_scratch = torch.empty((self.area_scratch_bytes + 7) // 8, dtype=f64, device=dev)
+        self._area_scratch = {}          # job range -> scratch of the persistent domain-growth grid (per CTA, not per job)
         self.area_work = torch.zeros((B_, _lib.SIE_AREA_WORK), dtype=torch.int64, device=dev)
         self.anomaly = torch.zeros((B_, MA, Ts), dtype=f64, device=dev)
         self.links = torch.zeros((B_, MA, MA), dtype=f64, device=dev)
@@ -140,8 +141,8 @@ class NetworkBatch:
         _lib.check(rc, "sie_detrend_zscore")
         self.launches += 3
 
-    def corr_tau(self, r_crit, store_R=True, shard_rank=0, shard_count=1, jr=None):
-        """K2.  r_crit: device float64 [B]."""
+    def corr_tau(self, r_crit, store_R=True, shard_rank=0, shard_count=1, jr=None, kernel=_lib.SIE_CORR_AUTO):
+        """K2.  r_crit: device float64 [B].  `kernel`: _lib.SIE_CORR_AUTO / _TILES / _ROWS (include/sie_b200.h)."""
         j0, j1 = self._range(jr)
         R = self.R[j0:] if store_R else None
         # each job range owns a disjoint slice of the tile-partial scratch so ranges can run concurrently
@@ -153,7 +154,7 @@ class NetworkBatch:
         rc = self.lib.sie_corr_tau(_ptr(self.z[j0:]), _ptr(self.n_nodes[j0:]), _ptr(self.job_T[j0:]),
                                    _ptr(r_crit[j0:]), j1 - j0, self.ldn, self.Tp, _ptr(R), _ptr(scratch),
                                    scratch.numel() * 8, _ptr(self.tau_sum[j0:]), _ptr(self.tau_cnt[j0:]),
-                                   _ptr(self.tau[j0:]), shard_rank, shard_count, _stream())
+                                   _ptr(self.tau[j0:]), shard_rank, shard_count, int(kernel), _stream())
         _lib.check(rc, "sie_corr_tau")
         self.launches += 5
 
@@ -165,17 +166,26 @@ class NetworkBatch:
                                        _ptr(self.n_nodes[j0:]), n, self.X, self.Y, self.ldn, int(self.latlon),
                                        _ptr(self.stencil[j0:]), _stream())
         _lib.check(rc, "sie_corr_stencil")
-        per_job = self.area_scratch_bytes // self.B          # sie_area_level_scratch_bytes is linear in B
-        scratch = self.area_scratch[j0 * per_job // 8:]
+        scratch = self._area_scratch.get((j0, j1))            # ranges may run concurrently: one scratch each
+        if scratch is None:
+            nbytes = int(self.lib.sie_area_level_scratch_bytes(n, self.C))
+            scratch = self._area_scratch[(j0, j1)] = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device="cuda")
         rc = self.lib.sie_area_level(_ptr(self.R[j0:]), _ptr(self.stencil[j0:]), _ptr(self.node_cell[j0:]),
                                      _ptr(self.cell_node[j0:]), _ptr(self.n_nodes[j0:]), _ptr(self.tau[j0:]),
                                      _ptr(self.first_nan[j0:]), n, self.X, self.Y, self.ldn, int(self.latlon),
                                      self.MA, _ptr(self.area_cells[j0:]), _ptr(self.area_start[j0:]),
                                      _ptr(self.area_key[j0:]), _ptr(self.n_areas[j0:]), _ptr(self.label[j0:]),
-                                     _ptr(self.status[j0:]), _ptr(scratch), n * per_job,
+                                     _ptr(self.status[j0:]), _ptr(scratch), scratch.numel() * 8,
                                      _ptr(self.area_work[j0:]), _stream())
         _lib.check(rc, "sie_area_level")
         self.launches += 2
+
+    def prepare(self, ranges=None):
+        """Allocate the per-range scratch up front (compute() may be captured into a CUDA graph: no allocation there)."""
+        for (j0, j1) in (ranges or [(0, self.B)]):
+            if (j0, j1) not in self._area_scratch and j1 > j0:
+                nbytes = int(self.lib.sie_area_level_scratch_bytes(j1 - j0, self.C))
+                self._area_scratch[(j0, j1)] = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device="cuda")
 
     def intra_links(self, scale, jr=None):
         """K6.  scale: device float64 [C] (already square-rooted weights)."""

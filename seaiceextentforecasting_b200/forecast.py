@@ -220,32 +220,42 @@ def mlii(theta, y, anoms_sic, anoms_sst=None, rule=0, alpha=0.05, zscore=False):
 class SweepPlan:
     """Host-only bookkeeping of a retrospective sweep: which network builds (jobs) and which GP problems exist,
     in the year/row indexing of the reference scripts (June1st_retro.py:199-290; south January1st_retro.py:173-182
-    for the previous-year variant).  `rank`/`world` shard whole (config, year) tasks -- a task owns its network
-    build(s) and its three regional forecasts, so shards exchange nothing."""
+    for the previous-year variant).  `members` > 1: an ensemble of input realisations (perturbed SIC / SST fields,
+    shared SIE targets; BASELINE.json configs[4]) in ONE batch -- member m's networks read field m * n_configs + ci.
+    `rank`/`world` shard whole (member, config, year) tasks -- a task owns its network build(s) and its three regional
+    forecasts, so shards exchange nothing."""
 
-    def __init__(self, config_names, sie, fmin, fmax, significance=0.01, rank=0, world=1):
+    def __init__(self, config_names, sie, fmin, fmax, significance=0.01, rank=0, world=1, members=1):
         self.cfgs = [CONFIGS[c] if isinstance(c, str) else c for c in config_names]
         self.fmin, self.fmax = int(fmin), int(fmax)
         self.years = list(range(self.fmin, self.fmax + 1))
         self.significance = significance
         self.rank, self.world = int(rank), int(world)
+        self.members = int(members)
         self.use_sst = any(c.use_sst for c in self.cfgs)
-        # tasks in a fixed global order, longest windows first so round-robin shards are balanced
-        tasks = [(ci, year) for year in reversed(self.years) for ci in range(len(self.cfgs))]
+        ncfg = len(self.cfgs)
+        # tasks in a fixed global order, longest windows first (the slowest network builds: the device pops jobs in
+        # this order, LPT) so round-robin shards are balanced too
+        tasks = [(m, ci, year) for year in reversed(self.years) for m in range(self.members) for ci in range(ncfg)]
         self.all_tasks = tasks
         self.tasks = [t for i, t in enumerate(tasks) if i % self.world == self.rank]
-        self.jobs, self.job_index = [], {}          # SIC network builds: (cfg index, network year)
-        self.sst_years = []                         # SST network builds (one per target year that needs it)
-        for ci, year in self.tasks:
+        self.jobs_m, self.job_index = [], {}        # SIC network builds: (member, cfg index, network year)
+        self.sst_jobs, self.sst_index = [], {}      # SST network builds: (member, target year)
+        for m, ci, year in self.tasks:
             cfg = self.cfgs[ci]
             ny = year - 1 if cfg.prev_year_network else year
-            if (ci, ny) not in self.job_index:
-                self.job_index[(ci, ny)] = len(self.jobs)
-                self.jobs.append((ci, ny))
-            if cfg.use_sst and year not in self.sst_years:
-                self.sst_years.append(year)
-        self.job_field = np.array([ci for ci, _ in self.jobs], dtype=np.int32)
-        self.job_T = np.array([ny - FIRST_YEAR + 1 for _, ny in self.jobs], dtype=np.int32)
+            if (m, ci, ny) not in self.job_index:
+                self.job_index[(m, ci, ny)] = len(self.jobs_m)
+                self.jobs_m.append((m, ci, ny))
+            if cfg.use_sst and (m, year) not in self.sst_index:
+                self.sst_index[(m, year)] = len(self.sst_jobs)
+                self.sst_jobs.append((m, year))
+        self.jobs = [(ci, ny) for _, ci, ny in self.jobs_m]          # (cfg index, network year) per SIC job
+        self.job_member = np.array([m for m, _, _ in self.jobs_m], dtype=np.int32)
+        self.sst_years = [y for _, y in self.sst_jobs]
+        self.sst_member = np.array([m for m, _ in self.sst_jobs], dtype=np.int32)
+        self.job_field = np.array([m * ncfg + ci for m, ci, _ in self.jobs_m], dtype=np.int32)
+        self.job_T = np.array([ny - FIRST_YEAR + 1 for _, _, ny in self.jobs_m], dtype=np.int32)
         self.rcrit = np.array([r_crit_ttest(int(T), significance) for T in self.job_T])
         self.sst_T = np.array([y - FIRST_YEAR + 1 for y in self.sst_years], dtype=np.int32)
         self.sst_rcrit = np.array([r_crit_ttest(int(T), significance) for T in self.sst_T])
@@ -253,9 +263,9 @@ class SweepPlan:
         self.sie_dt, self.sie_trend = {}, {}
         for reg, series in self.sie.items():
             self.sie_dt[reg], self.sie_trend[reg] = sie_detrend_tables(series, self.fmin, self.fmax)
-        probs, ys, self.prob_meta = [], [], []
+        probs, ys, self.prob_meta, prob_member = [], [], [], []
         y_off = 0
-        for ci, year in self.tasks:
+        for m, ci, year in self.tasks:
             cfg = self.cfgs[ci]
             for k, reg in enumerate(cfg.regions):
                 row = year - (self.fmin - 1) - 1
@@ -266,8 +276,8 @@ class SweepPlan:
                 n = y.size
                 ny = year - 1 if cfg.prev_year_network else year
                 p = np.zeros(1, dtype=GP_PROBLEM_DTYPE)
-                p["job_sic"] = self.job_index[(ci, ny)]
-                p["job_sst"] = self.sst_years.index(year) if cfg.use_sst else -1
+                p["job_sic"] = self.job_index[(m, ci, ny)]
+                p["job_sst"] = self.sst_index[(m, year)] if cfg.use_sst else -1
                 p["n"] = n
                 p["y_off"] = y_off
                 p["rule"] = cfg.rule[k]
@@ -279,6 +289,8 @@ class SweepPlan:
                 ys.append(y)
                 y_off += n
                 self.prob_meta.append((ci, k, year))
+                prob_member.append(m)
+        self.prob_member = np.array(prob_member, dtype=np.int32)
         self.prob = np.concatenate(probs) if probs else np.zeros(0, dtype=GP_PROBLEM_DTYPE)
         self.y = np.concatenate(ys) if ys else np.zeros(0)
         self.P = len(probs)
@@ -296,14 +308,23 @@ class SweepPlan:
             splits.append(int(p0 + (~uses).sum()))
         self.prob = np.ascontiguousarray(self.prob[perm])
         self.prob_meta = [self.prob_meta[i] for i in perm]
+        self.prob_member = self.prob_member[perm]
         return splits
 
-    def assemble(self, raw, meta=None):
+    def assemble(self, raw, meta=None, member=None):
         """-> {config: {region_fmean / _fvar / _fmean_rt: array(years)}} like the reference's GPR dict
         (June1st_retro.py:284-290, rounded to 3 d.p.), the un-rounded values under '<region>_raw_*'.
-        `raw`/`meta` may be the concatenation over all ranks (after a gather)."""
+        `raw`/`meta`/`member` may be the concatenation over all ranks (after a gather).  With `members` > 1 the result
+        is a list of such dicts, one per ensemble member."""
         meta = self.prob_meta if meta is None else meta
+        member = self.prob_member if member is None else np.asarray(member)
         raw = np.asarray(raw)
+        if self.members > 1:
+            marr = np.asarray(meta, dtype=np.int64).reshape(-1, 3)
+            return [self._assemble_one(raw[member == mm], marr[member == mm]) for mm in range(self.members)]
+        return self._assemble_one(raw, meta)
+
+    def _assemble_one(self, raw, meta):
         m = np.asarray(meta, dtype=np.int64).reshape(-1, 3)
         out = {}
         if m.shape[0] == 0:
@@ -349,8 +370,11 @@ class SweepPlan:
 class RetrospectiveSweep:
     """years fmin..fmax x the given init-month configs x 3 regions, in one device-resident batch.
 
-    sic_fields : dict config-name -> (X, Y, Tfull) raw monthly SIC of that init's data month
-    sst_field  : (Xs, Ys, Tfull) raw May SST (only used by configs with use_sst) or None
+    sic_fields : dict config-name -> (X, Y, Tfull) raw monthly SIC of that init's data month, or a LIST of such dicts:
+                 one per ensemble member (perturbed realisations, BASELINE.json configs[4]); all members run in one
+                 device batch, so the latency-bound domain-growth chains of different members overlap
+    sst_field  : (Xs, Ys, Tfull) raw May SST (only used by configs with use_sst) or None; a list (one per member) when
+                 sic_fields is a list
     sie        : dict region -> (Tfull,) September (or target-month) extent
     psar / sst_lat : weights for intra_links (cell area for the polar grid, latitude grid for SST)
     """
@@ -358,25 +382,34 @@ class RetrospectiveSweep:
     def __init__(self, config_names, sic_fields, sie, fmin, fmax, psar, sst_field=None, sst_lat=None,
                  significance=0.01, max_areas=None, max_pred=384, rank=0, world=1, wave_T=(12,)):
         require_cuda()
-        self.plan = plan = SweepPlan(config_names, sie, fmin, fmax, significance, rank, world)
+        member_fields = list(sic_fields) if isinstance(sic_fields, (list, tuple)) else [sic_fields]
+        self.members = len(member_fields)
+        self.plan = plan = SweepPlan(config_names, sie, fmin, fmax, significance, rank, world, members=self.members)
         self.cfgs, self.years, self.fmin, self.fmax = plan.cfgs, plan.years, plan.fmin, plan.fmax
-        first = np.asarray(sic_fields[self.cfgs[0].name])
+        first = np.asarray(member_fields[0][self.cfgs[0].name])
         self.X, self.Y, self.Tfull = first.shape
         assert self.Tfull >= self.fmax - FIRST_YEAR + 1
-        self.sic_host = np.stack([np.ascontiguousarray(sic_fields[c.name], dtype=np.float64).reshape(
-            self.X * self.Y, self.Tfull) for c in self.cfgs])
+        self.sic_host = np.stack([np.ascontiguousarray(mf[c.name], dtype=np.float64).reshape(
+            self.X * self.Y, self.Tfull) for mf in member_fields for c in self.cfgs])      # [member * n_configs + ci]
         self.psar_host = np.sqrt(np.asarray(psar, dtype=np.float64)).reshape(-1)     # ComplexNetworks.py:298-299
         self.use_sst = plan.use_sst and len(plan.sst_years) > 0
-        n_upper = int(max((~np.isnan(f).any(axis=1)).sum() for f in self.sic_host))
+        # node capacity: a cell is a node of window T when its first T samples are NaN-free (detrend() fits the prefix),
+        # so the count is largest for the SHORTEST window of the sweep -- a cell whose only NaN lies in a later year
+        # is a node of the early windows
+        Tmin = int(plan.job_T.min()) if len(plan.job_T) else self.Tfull
+        n_upper = int(max((~np.isnan(f[:, :Tmin]).any(axis=1)).sum() for f in self.sic_host))
         self.sic = NetworkBatch(self.X, self.Y, self.Tfull, max(1, len(plan.jobs)), latlon=False, n_upper=n_upper,
                                 max_areas=max_areas)
         self.sst = None
         if self.use_sst:
-            s = np.ascontiguousarray(sst_field, dtype=np.float64)
-            self.Xs, self.Ys = s.shape[0], s.shape[1]
-            self.sst_host = s.reshape(1, self.Xs * self.Ys, self.Tfull)
+            sst_members = list(sst_field) if isinstance(sst_field, (list, tuple)) else [sst_field] * self.members
+            assert len(sst_members) == self.members
+            s = np.stack([np.ascontiguousarray(f, dtype=np.float64) for f in sst_members])
+            self.Xs, self.Ys = s.shape[1], s.shape[2]
+            self.sst_host = s.reshape(self.members, self.Xs * self.Ys, self.Tfull)
             self.lat_host = np.sqrt(np.cos(np.radians(np.asarray(sst_lat, dtype=np.float64)))).reshape(-1)  # :296-297
-            n_up = int((~np.isnan(self.sst_host[0]).any(axis=1)).sum())
+            Tmin_s = int(plan.sst_T.min())
+            n_up = int(max((~np.isnan(f[:, :Tmin_s]).any(axis=1)).sum() for f in self.sst_host))
             self.sst = NetworkBatch(self.Xs, self.Ys, self.Tfull, len(plan.sst_years), latlon=True, n_upper=n_up,
                                     max_areas=max_areas)
         self.P = plan.P
@@ -443,7 +476,7 @@ class RetrospectiveSweep:
              "psar": self.psar_host, "prob": p.prob.view(np.uint8), "y": p.y}
         if self.use_sst:
             d.update({"sst": self.sst_host, "sst_T": p.sst_T, "sst_rcrit": p.sst_rcrit, "lat": self.lat_host,
-                      "sst_field_idx": np.zeros(len(p.sst_years), dtype=np.int32)})
+                      "sst_field_idx": p.sst_member.astype(np.int32)})
         return d
 
     def h2d_bytes(self):
@@ -609,8 +642,10 @@ class RetrospectiveSweep:
         return int(n)
 
     def download(self):
-        """Device -> host read of the GP results (synchronises)."""
+        """Device -> host read of the GP results (synchronises).  Raises if any network build or GP problem ran out of
+        the capacity this sweep was sized for (a silent NaN forecast would look like a reference failure)."""
         self.raw = self.gp.results()[:self.P]
+        self.check_status(self.raw)
         return self.raw
 
     def run(self):
@@ -631,6 +666,8 @@ class RetrospectiveSweep:
         def finish(ev, buf):
             ev.synchronize()
             self.raw = buf.numpy().view(GP_RESULT_DTYPE)[:self.P].copy()    # the buffer is reused two steps later
+            if (self.raw["info"] == -2).any():
+                self.check_status(self.raw)
             return self.plan.assemble(self.raw)
 
         for i in range(int(n)):
@@ -645,10 +682,24 @@ class RetrospectiveSweep:
             pending = (ev, buf)
         if pending is not None:
             yield finish(*pending)
+        self.check_status()                    # every step ran the same inputs: one check of the job statuses suffices
 
-    def check_status(self):
+    def check_status(self, raw=None):
+        """Raises SieError when a network build exceeded the node / area capacity (status SIE_JOB_CAPACITY, SIC or SST
+        engine) or a GP problem the predictor capacity `max_pred` (info = -2); returns the SIC status array.  A job
+        over capacity produces no areas, so its forecasts come back as info = -1 / NaN: indistinguishable from a
+        reference failure unless checked here."""
         st = self.sic.status.cpu().numpy()
-        bad = np.nonzero(st == _lib.SIE_JOB_CAPACITY)[0]
-        if bad.size:
-            raise _lib.SieError(f"capacity exceeded in SIC jobs {bad.tolist()}")
+        for tag, eng in (("SIC", self.sic), ("SST", self.sst)):
+            if eng is None:
+                continue
+            bad = np.nonzero(eng.status.cpu().numpy() == _lib.SIE_JOB_CAPACITY)[0]
+            if bad.size:
+                raise _lib.SieError(f"capacity exceeded in {tag} network builds {bad.tolist()[:8]} (nodes > {eng.ldn} "
+                                    f"or areas > {eng.MA}): construct the sweep with larger capacities")
+        if raw is not None:
+            bad = np.nonzero(np.asarray(raw["info"]) == -2)[0]
+            if bad.size:
+                raise _lib.SieError(f"GP problems {bad.tolist()[:8]} selected more than max_pred = {self.gp.max_pred} "
+                                    "predictors (or n + 1 > 64 samples): construct the sweep with a larger max_pred")
         return st

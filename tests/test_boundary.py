@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(lib_built):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/sie_b200.h but not exported"
     assert set(names) == set(_lib.EXPORTED_SYMBOLS)
-    assert _lib.load().sie_abi_version() == 1
+    assert _lib.load().sie_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_library_is_sm100a_only(lib_built):

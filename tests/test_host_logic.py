@@ -93,24 +93,25 @@ def test_shards_partition_the_sweep():
 
 def _worker(rank, world, port, q):
     import torch.distributed as dist
+    from seaiceextentforecasting_b200 import parallel
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    plan = SweepPlan(NORTH_INITS, _sie(), 2015, 2020, rank=rank, world=world)
-    raw = np.zeros(plan.P, dtype=GP_RESULT_DTYPE)
-    for i, (ci, k, year) in enumerate(plan.prob_meta):               # fake kernel output: encodes the problem id
-        raw["fmean"][i] = ci * 1000 + k * 100 + (year - 2000)
-    gathered = [None] * world
-    dist.all_gather_object(gathered, (plan.prob_meta, raw.tobytes()))
+    ok = True
+    for members in (1, 3):                                           # 3 members: ranks own unequal problem counts
+        plan = SweepPlan(NORTH_INITS, _sie(), 2015, 2020, rank=rank, world=world, members=members)
+        raw = np.zeros(plan.P, dtype=GP_RESULT_DTYPE)
+        for i, ((ci, k, year), m) in enumerate(zip(plan.prob_meta, plan.prob_member)):   # fake kernel output = problem id
+            raw["fmean"][i] = m * 10000 + ci * 1000 + k * 100 + (year - 2000)
+        out = parallel.gather_results(plan, raw)                     # tensor all-gather of the 80-byte records
+        outs = out if members > 1 else [out]
+        assert len(outs) == members
+        for m, o in enumerate(outs):
+            for ci, cfg in enumerate(plan.cfgs):
+                for k, reg in enumerate(cfg.regions):
+                    exp = np.array([m * 10000 + ci * 1000 + k * 100 + (y - 2000) for y in plan.years], dtype=float)
+                    ok &= np.array_equal(o[cfg.name][reg + "_raw_fmean"], exp)
     if rank == 0:
-        meta = [m for g in gathered for m in g[0]]
-        allraw = np.concatenate([np.frombuffer(g[1], dtype=GP_RESULT_DTYPE) for g in gathered])
-        out = plan.assemble(allraw, meta)
-        ok = True
-        for ci, cfg in enumerate(plan.cfgs):
-            for k, reg in enumerate(cfg.regions):
-                exp = np.array([ci * 1000 + k * 100 + (y - 2000) for y in plan.years], dtype=float)
-                ok &= np.array_equal(out[cfg.name][reg + "_raw_fmean"], exp)
-        q.put(ok)
+        q.put(bool(ok))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -204,9 +204,9 @@ def test_row_sharded_tau_matches_unsharded_and_numpy(lib_built):
 
 @pytest.mark.parametrize("X,Y,Ts,latlon", [(20, 22, [7, 12, 30, 42], False), (57, 57, [7, 25, 42], False),
                                            (26, 90, [9, 42], True), (81, 81, [33], False)])
-def test_both_correlation_kernels_agree(lib_built, monkeypatch, X, Y, Ts, latlon):
+def test_both_correlation_kernels_agree(lib_built, X, Y, Ts, latlon):
     """`sie_corr_tau` has two kernels (csrc/corr.cu): the tile kernel (default when R is stored) and the row-resident,
-    warp-specialised one (default for the tau-only pass).  Either can serve either mode (SIE_CORR_KERNEL): R must be
+    warp-specialised one (default for the tau-only pass).  Either can serve either mode (the `kernel` argument): R must be
     bitwise identical, bitwise symmetric with a NaN diagonal, the count identical and tau within 1e-12; R also matches
     numpy's corrcoef of the detrended nodes to 1e-9 (ComplexNetworks.py:34-35)."""
     import torch
@@ -223,14 +223,14 @@ def test_both_correlation_kernels_agree(lib_built, monkeypatch, X, Y, Ts, latlon
     torch.cuda.synchronize()
     N = eng.n_nodes.cpu().numpy()
     out = {}
-    for kern in ("tiles", "rows"):
-        monkeypatch.setenv("SIE_CORR_KERNEL", kern)
+    from seaiceextentforecasting_b200 import _lib
+    for kern, kid in (("tiles", _lib.SIE_CORR_TILES), ("rows", _lib.SIE_CORR_ROWS)):
         eng.R.fill_(-7.0)
-        eng.corr_tau(rc, store_R=True)
+        eng.corr_tau(rc, store_R=True, kernel=kid)
         torch.cuda.synchronize()
         Rs = [eng.R[b, :N[b], :N[b]].cpu().numpy().copy() for b in range(B)]
         stored = (eng.tau.cpu().numpy().copy(), eng.tau_cnt.cpu().numpy().copy())
-        eng.corr_tau(rc, store_R=False)
+        eng.corr_tau(rc, store_R=False, kernel=kid)
         torch.cuda.synchronize()
         out[kern] = (Rs, stored, (eng.tau.cpu().numpy().copy(), eng.tau_cnt.cpu().numpy().copy()))
     for b in range(B):
@@ -250,7 +250,7 @@ def test_both_correlation_kernels_agree(lib_built, monkeypatch, X, Y, Ts, latlon
     np.testing.assert_allclose(out["rows"][1][0], out["rows"][2][0], rtol=1e-12)
 
 
-def test_full_size_25km_correlation_properties(lib_built, monkeypatch):
+def test_full_size_25km_correlation_properties(lib_built):
     """BASELINE.json configs[3] at its full size (448x304 grid, T = 42, ~63 k nodes; the oracle cannot run it: R would be
     32 GB) through size-independent properties of `sie_corr_tau` with R not stored: the (sum, count) partials of 8 row
     shards add up to the unsharded result (count exactly), both kernels count the same pairs and agree on tau, and tau is
@@ -268,12 +268,11 @@ def test_full_size_25km_correlation_properties(lib_built, monkeypatch):
     rc = h2d(np.array([rcv]))
     eng.detrend_zscore(f, jf, jT, True)
     res = {}
-    for kern in ("rows", "tiles"):
-        monkeypatch.setenv("SIE_CORR_KERNEL", kern)
-        eng.corr_tau(rc, store_R=False)
+    from seaiceextentforecasting_b200 import _lib
+    for kern, kid in (("rows", _lib.SIE_CORR_ROWS), ("tiles", _lib.SIE_CORR_TILES)):
+        eng.corr_tau(rc, store_R=False, kernel=kid)
         torch.cuda.synchronize()
         res[kern] = (eng.tau_sum.item(), eng.tau_cnt.item(), eng.tau.item())
-    monkeypatch.delenv("SIE_CORR_KERNEL")
     N = int(eng.n_nodes.item())
     assert N > 60000
     s_all, c_all, tau_all = res["rows"]

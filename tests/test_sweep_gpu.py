@@ -23,9 +23,21 @@ def unpack_V(g, suffix=""):
     return V
 
 
-def gp_tol(rec):
-    """1e-9 relative, widened by the documented 2^s amplification of expm's squaring phase."""
-    return max(1e-9, 64.0 * 2.0 ** int(rec["expm_s"]) * 2.0 ** -53)
+def gp_tol(rec, cond):
+    """1e-9 relative (north_star), widened only by the conditioning of the reference's own arithmetic: expm's s
+    squarings amplify rounding by ~2^s (scipy itself moves that much under a 1-ulp input perturbation,
+    tests/test_expm_spec.py) and two backward-stable Cholesky solves differ by ~cond(K) eps (`cond` is
+    the oracle's 2-norm condition number of the kernel matrix)."""
+    return max(1e-9, 64.0 * 2.0 ** int(rec["expm_s"]) * 2.0 ** -53, 8.0 * float(cond) * 2.0 ** -53)
+
+
+def oracle_sweep(cfgs, sic, sie, fmin, fmax, psar, sst=None, lat=None):
+    import warnings
+
+    from oracle import sweep as osweep
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return osweep.retro_sweep(cfgs, sic, sie, fmin, fmax, psar, sst, lat, record_failures=True)
 
 
 @pytest.mark.parametrize("path", SWEEPS, ids=[os.path.basename(p) for p in SWEEPS])
@@ -41,34 +53,46 @@ def test_sweep_matches_reference_golden(lib_built, path):
     out = sw.run()
     raw = sw.raw
     assert (raw["info"] == 0).all()
+    # condition numbers for the tolerance come from the oracle run on the same inputs (seconds at this size); its
+    # forecasts must equal the golden ones (the oracle is pinned: tests/test_oracle_golden.py)
+    ora = oracle_sweep([cfg], {name: g["sic"]}, sie, fmin, fmax, g["psar"], g["sst"] if cfg.use_sst else None,
+                       g["sst_lat"] if cfg.use_sst else None)[name]
     # every network of the sweep: bit-exact area membership and order
     for (st, V), (ci, ny) in zip(sw.sic.areas_to_host(), sw.plan.jobs):
         assert st == 0
         assert V == unpack_V(g, f"_{ny}"), ny
     for k, reg in enumerate(cfg.regions):
-        for suf in ("_fmean", "_fvar", "_fmean_rt"):
-            ref = g["raw_" + reg + suf]
-            got = out[name][reg + "_raw" + suf]
-            for i, year in enumerate(sw.years):
-                rec = raw[sw.plan.prob_meta.index((0, k, year))]
-                scale = max(abs(ref[i]), 1e-2)
-                assert abs(got[i] - ref[i]) <= 50 * gp_tol(rec) * scale, (reg, suf, year, got[i], ref[i], rec)
+        for i, year in enumerate(sw.years):
+            rec = raw[sw.plan.prob_meta.index((0, k, year))]
+            t = gp_tol(rec, ora[reg + "_cond"][i])
+            rf, rv, rrt = (g["raw_" + reg + suf][i] for suf in ("_fmean", "_fvar", "_fmean_rt"))
+            # natural scale of the predictive mean: itself or the predictive standard deviation (the mean is a sum of
+            # O(sqrt(fvar))-sized terms that may cancel); of the variance: itself
+            scale = max(abs(rf), np.sqrt(abs(rv)))
+            assert abs(out[name][reg + "_raw_fmean"][i] - rf) <= t * scale, (reg, year, rec, rf)
+            assert abs(out[name][reg + "_raw_fvar"][i] - rv) <= t * max(abs(rv), scale ** 2), (reg, year, rec, rv)
+            assert abs(out[name][reg + "_raw_fmean_rt"][i] - rrt) <= t * max(scale, abs(rrt)), (reg, year, rec, rrt)
             # the reference's own output format: rounded to 3 d.p. -- checked wherever the conditioning-aware bound
             # is itself below the rounding step (July/Chukchi's l = 3.1e10 needs s ~ 56 squarings: scipy's own
             # result moves in the 3rd decimal under a 1-ulp input perturbation, tests/test_expm_spec.py)
-            rnd = g["rnd_" + reg + suf]
-            for i, year in enumerate(sw.years):
-                rec = raw[sw.plan.prob_meta.index((0, k, year))]
-                if 50 * gp_tol(rec) * max(abs(ref[i]), 1e-2) < 5e-4:
-                    assert abs(out[name][reg + suf][i] - rnd[i]) <= 1.0e-3 + 1e-12, (reg, suf, year)
+            if t * max(scale, abs(rrt)) < 5e-4:
+                for suf in ("_fmean", "_fvar", "_fmean_rt"):
+                    assert abs(out[name][reg + suf][i] - g["rnd_" + reg + suf][i]) <= 1.0e-3 + 1e-12, (reg, suf, year)
+    # skill() is a 3-d.p. output computed from the 3-d.p. forecasts: one unit in the last place (a forecast within the
+    # bound above of a rounding boundary can move one digit) wherever every forecast of the region is well conditioned
     sk = sw.plan.skill(out)[name]
-    assert np.all(np.abs(np.array(sk[0]) - g["skill_rt"]) <= 0.02)
-    assert np.all(np.abs(np.array(sk[1]) - g["skill_dt"]) <= 0.02)
+    for k, reg in enumerate(cfg.regions):
+        recs = [raw[sw.plan.prob_meta.index((0, k, year))] for year in sw.years]
+        if max(gp_tol(r, c) for r, c in zip(recs, ora[reg + "_cond"])) * 10.0 < 5e-4:
+            assert abs(sk[0][k] - g["skill_rt"][k]) <= 1e-3 + 1e-12, (reg, sk[0][k], g["skill_rt"][k])
+            assert abs(sk[1][k] - g["skill_dt"][k]) <= 1e-3 + 1e-12, (reg, sk[1][k], g["skill_dt"][k])
 
 
 def test_multi_init_north_sweep_matches_oracle(lib_built):
-    """All four north inits + SST in one batch (the bench's structure at a size the oracle finishes in seconds)."""
-    from oracle import sweep as osweep
+    """All four north inits + SST in one batch (the bench's structure -- cross-config job indices, waves on separate
+    streams, the SST-partitioned problem order -- at a size the oracle finishes in seconds).  Where the reference's
+    forecast() raises (fewer than two predictors pass the selection rule) the kernel must report info = -1 for exactly
+    that (config, region, year) and everything else must still match."""
     from seaiceextentforecasting_b200.forecast import RetrospectiveSweep
     fmin, fmax = 1993, 1996
     Tfull = fmax - 1979 + 1
@@ -81,24 +105,31 @@ def test_multi_init_north_sweep_matches_oracle(lib_built):
     sie = dict(zip(CONFIGS["north_june"].regions, sie0))
     sst, _ = syn.make_field(8, 18, Tfull, 399, latlon=True, saturate=False, n_modes=20, noise=0.5, blob=(1.0, 2.5))
     psar, lat = syn.make_psar(15, 15), syn.make_lat_grid(8, 18)
-    sw = RetrospectiveSweep(NORTH_INITS, sic, sie, fmin, fmax, psar, sst, lat)
+    sw = RetrospectiveSweep(NORTH_INITS, sic, sie, fmin, fmax, psar, sst, lat, wave_T=(16,))
+    assert sw.multi_wave                       # the multi-stream schedule is what is being tested
     out = sw.run()
     cfgs = [CONFIGS[n] for n in NORTH_INITS]
-    try:
-        ora = osweep.retro_sweep(cfgs, sic, sie, fmin, fmax, psar, sst, lat)
-    except (ValueError, IndexError, np.linalg.LinAlgError) as e:      # the reference crashes on <2 predictors
-        pytest.skip(f"oracle/reference raises on this input: {e}")
+    ora = oracle_sweep(cfgs, sic, sie, fmin, fmax, psar, sst, lat)
     for (st, V), (ci, ny) in zip(sw.sic.areas_to_host(), sw.plan.jobs):
         assert V == ora[cfgs[ci].name]["V"][ny]
+    n_ok = n_fail = 0
     for ci, cfg in enumerate(cfgs):
         for k, reg in enumerate(cfg.regions):
             for i, year in enumerate(sw.years):
                 rec = sw.raw[sw.plan.prob_meta.index((ci, k, year))]
-                assert rec["info"] == 0
-                for suf in ("_fmean", "_fvar"):
-                    ref = ora[cfg.name][reg + suf][i]
-                    got = out[cfg.name][reg + "_raw" + suf][i]
-                    assert abs(got - ref) <= 50 * gp_tol(rec) * max(abs(ref), 1e-2), (cfg.name, reg, year, got, ref)
+                if ora[cfg.name][reg + "_failed"][i] is not None:
+                    assert rec["info"] == -1, (cfg.name, reg, year, rec)
+                    assert np.isnan(out[cfg.name][reg + "_raw_fmean"][i])
+                    n_fail += 1
+                    continue
+                assert rec["info"] == 0, (cfg.name, reg, year, rec)
+                n_ok += 1
+                t = gp_tol(rec, ora[cfg.name][reg + "_cond"][i])
+                rf, rv = ora[cfg.name][reg + "_fmean"][i], ora[cfg.name][reg + "_fvar"][i]
+                scale = max(abs(rf), np.sqrt(abs(rv)))      # the predictive standard deviation is the mean's scale
+                assert abs(out[cfg.name][reg + "_raw_fmean"][i] - rf) <= t * scale, (cfg.name, reg, year, rec, rf)
+                assert abs(out[cfg.name][reg + "_raw_fvar"][i] - rv) <= t * max(abs(rv), scale ** 2), (cfg.name, reg, year)
+    assert n_ok >= 30 and n_fail >= 1 and n_ok + n_fail == 48
 
 
 def test_sweep_hyper_grid_contains_the_script_settings(lib_built):
@@ -198,7 +229,9 @@ def test_full_size_north_sweep_invariants(lib_built):
             acc = acc + dt0[c, :T0] * scale[c]
         assert np.array_equal(eng.anomaly[0, 0, :T0].cpu().numpy(), acc)
     bad = raw["info"] != 0
-    assert bad.sum() <= 2
+    # the only non-zero info is -1 = "the reference's forecast() raises" (fewer than two predictors selected): the 6
+    # (north_august, Chukchi) problems tests/golden/bench_north_m0.npz records for this workload
+    assert (raw["info"][bad] == -1).all() and bad.sum() == 6
     ok = ~bad
     assert np.isfinite(raw["fmean"][ok]).all() and (raw["fvar"][ok] > 0).all()
     sw.run()

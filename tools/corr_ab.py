@@ -1,8 +1,11 @@
-"""A/B of the two correlation kernels (SIE_CORR_KERNEL=tiles|rows): R bitwise, tau, time.  Stored-R sweep shape + 25 km tau-only."""
+"""A/B of the two correlation kernels (the `kernel` argument of sie_corr_tau): R bitwise, tau, time.  Stored-R sweep shape + 25 km tau-only."""
 import sys, os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from seaiceextentforecasting_b200 import synthetic as syn
+from seaiceextentforecasting_b200 import _lib
 from seaiceextentforecasting_b200.engine import NetworkBatch, h2d, r_crit_ttest
+
+KERNELS = (("tiles", _lib.SIE_CORR_TILES), ("rows", _lib.SIE_CORR_ROWS))
 
 
 def timed(fn, reps=5):
@@ -26,14 +29,13 @@ def stored(X, Y, Ts, latlon=False):
     rc = h2d(np.array([r_crit_ttest(t, 0.01) for t in Ts]))
     eng.detrend_zscore(fields, jf, jT, True); torch.cuda.synchronize()
     out = {}
-    for kern in ("tiles", "rows"):
-        os.environ["SIE_CORR_KERNEL"] = kern
+    for kern, kid in KERNELS:
         eng.R.fill_(-7.0)
-        eng.corr_tau(rc, store_R=True); torch.cuda.synchronize()
+        eng.corr_tau(rc, store_R=True, kernel=kid); torch.cuda.synchronize()
         N = eng.n_nodes.cpu().numpy()
         out[kern] = ([eng.R[b, :N[b], :N[b]].cpu().numpy().copy() for b in range(min(B, 6))], eng.tau.cpu().numpy().copy(),
                      eng.tau_cnt.cpu().numpy().copy())
-        ms = timed(lambda: eng.corr_tau(rc, store_R=True))
+        ms = timed(lambda: eng.corr_tau(rc, store_R=True, kernel=kid))
         byts = float((8.0 * N.astype(np.float64) ** 2).sum())
         print(f"{X}x{Y} B={B} {kern}: {ms:.3f} ms  {byts/ms/1e6:.0f} GB/s stored (8N^2)  N={N[0]} ldn={eng.ldn}")
     for b, (a, c) in enumerate(zip(out["tiles"][0], out["rows"][0])):
@@ -57,16 +59,15 @@ def tau_only():
     eng.detrend_zscore(fields, jf, jT, True); torch.cuda.synchronize()
     N = int(eng.n_nodes.item())
     res = {}
-    for kern in ("tiles", "rows"):
-        os.environ["SIE_CORR_KERNEL"] = kern
+    for kern, kid in KERNELS:
         for shards in (1, 8):
-            ms = timed(lambda: eng.corr_tau(rc, store_R=False, shard_rank=0, shard_count=shards), reps=3)
+            ms = timed(lambda: eng.corr_tau(rc, store_R=False, shard_rank=0, shard_count=shards, kernel=kid), reps=3)
             print(f"25km {kern} shards={shards}: {ms:.2f} ms {N*(N+1.0)*T/shards/ms/1e9:.2f} TFLOP/s")
-        eng.corr_tau(rc, store_R=False); torch.cuda.synchronize()
+        eng.corr_tau(rc, store_R=False, kernel=kid); torch.cuda.synchronize()
         res[kern] = (eng.tau_sum.item(), eng.tau_cnt.item())
         ss, cc = 0.0, 0
         for r in range(4):
-            eng.corr_tau(rc, store_R=False, shard_rank=r, shard_count=4); torch.cuda.synchronize(); ss += eng.tau_sum.item(); cc += eng.tau_cnt.item()
+            eng.corr_tau(rc, store_R=False, shard_rank=r, shard_count=4, kernel=kid); torch.cuda.synchronize(); ss += eng.tau_sum.item(); cc += eng.tau_cnt.item()
         print(f"  {kern}: unsharded {res[kern]}  4 shards {ss, cc}")
         assert cc == res[kern][1]
     assert res["tiles"][1] == res["rows"][1]
@@ -82,4 +83,3 @@ if __name__ == "__main__":
     stored(57, 57, [7 + (i * 35) // 23 for i in range(24)])
     stored(26, 90, [9, 42], latlon=True)
     tau_only()
-    os.environ.pop("SIE_CORR_KERNEL", None)
