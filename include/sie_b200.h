@@ -93,12 +93,21 @@ int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32_t* job_T, 
                  int shard_rank, int shard_count, int kernel, void* stream);
 size_t sie_corr_tau_scratch_bytes(int B, int ldn);
 
+/* Selected rows of the correlation matrix of ONE network recomputed from its unit-norm rows z [ldn][Tp] (N nodes, window
+ * T): out[r][c] = R[rows[r]][c], NaN on the diagonal.  Serves the `corrs[n]` accessor of the drop-in Network when R is not
+ * stored (ComplexNetworks.py:36-39 scatters exactly these rows).  rows [n_rows] device int32; out [n_rows][ld_out]. */
+int sie_corr_rows(const double* z, const int32_t* rows, int n_rows, int N, int T, int Tp, double* out, int ld_out,
+                  void* stream);
+
 /* K3  local stencil: correlation of every node with its 4 von-Neumann neighbours (up,down,left,right;
  *     lat-lon wrap in the second axis), NaN where the neighbour is off-grid or not a node.
  * Replaces: the seed search gathers `corrs[ID,nei]`            ComplexNetworks.py:166-172, :53-78
+ * R        [B][ldn][ldn], or NULL: the 4 correlations are then recomputed from the unit-norm rows
+ *          z [B][ldn][Tp] (job_T [B] = window lengths) -- no stored matrix is needed (25 km grids)
  * stencil  [B][ldn][4]
  */
-int sie_corr_stencil(const double* R, const int32_t* node_cell, const int32_t* cell_node,
+int sie_corr_stencil(const double* R, const double* z, const int32_t* job_T, int Tp,
+                     const int32_t* node_cell, const int32_t* cell_node,
                      const int32_t* n_nodes, int B, int X, int Y, int ldn, int latlon,
                      double* stencil, void* stream);
 
@@ -106,12 +115,19 @@ int sie_corr_stencil(const double* R, const int32_t* node_cell, const int32_t* c
  * K4+K5  tau-thresholded domain growth (step 1) and largest-first merging (step 2); one persistent
  *        CTA per network, numpy-pairwise-order means so decisions are those of the reference.
  * Replaces: Network.area_level                                 ComplexNetworks.py:49-278
+ * R          [B][ldn][ldn] correlations (K2), or NULL: every correlation the growth / merge decisions consume is then
+ *            recomputed from the unit-norm rows z [B][ldn][Tp] (42 FMAs each; z stays L2-resident), so a network
+ *            whose N x N matrix does not fit in HBM can still be built.  job_T [B], Tp: as for K1/K2 (only read
+ *            when R == NULL).  Jobs are popped from a queue in index order by a persistent grid: put the slowest
+ *            (longest-window) jobs first.  The job statuses written by K1 are read here (a job K1 flagged
+ *            SIE_JOB_CAPACITY is skipped), so K1 must have run on the same `status` array.
  * area_cells [B][C]  member cells, area after area in dict order, each area in its list order
  * area_start [B][max_areas+1], area_key [B][max_areas] (the reference's dict keys), n_areas [B]
  * label      [B][C]  index into area_key (dict position) or -1
  * status     [B]  SIE_JOB_* (areas are still written when status == SIE_JOB_FEW_AREAS, like the
  *            reference leaves V populated when it raises at :278)
- * scratch    at least sie_area_level_scratch_bytes(B, X*Y) bytes
+ * scratch    at least sie_area_level_scratch_bytes(B, X*Y) bytes: the job-queue counter + one block per CTA of the
+ *            persistent grid (NOT per job); concurrent calls need disjoint scratch
  * work       [B][SIE_AREA_WORK] or NULL: per job {0: correlations consumed (the algorithmic gather count, 8 B
  *            each), 1: SM cycles in step 1, 2: SM cycles in step 2, 3: (growth steps << 32) | merge rounds,
  *            4..14: SM cycles per phase (step 1: seed search, evaluate+argmax, frontier update, gathers;
@@ -119,7 +135,8 @@ int sie_corr_stencil(const double* R, const int32_t* node_cell, const int32_t* c
  *            merge/finalise; 14 unused), 15: growth steps that took the re-summing path}; the per-phase entries
  *            4..14 and 16..25 are only filled by a build with -DSIE_AREA_PHASE_TIMERS (they cost ~6 % of the kernel)
  */
-int sie_area_level(const double* R, const double* stencil, const int32_t* node_cell,
+int sie_area_level(const double* R, const double* z, const int32_t* job_T, int Tp,
+                   const double* stencil, const int32_t* node_cell,
                    const int32_t* cell_node, const int32_t* n_nodes, const double* tau,
                    const int32_t* first_nan_cell, int B, int X, int Y, int ldn, int latlon,
                    int max_areas, int32_t* area_cells, int32_t* area_start, int32_t* area_key,

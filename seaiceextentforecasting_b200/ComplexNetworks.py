@@ -21,6 +21,10 @@ from .engine import NetworkBatch, h2d, r_crit_ttest, require_cuda
 
 
 class Network:
+    # Largest correlation matrix (bytes) the class keeps on the device; above it `tau` runs the tau-only correlation
+    # pass and `area_level` recomputes the correlations it needs from the unit-norm rows (a 25 km grid: 32-148 GB).
+    max_matrix_bytes = 24 << 30
+
     def __init__(self, data, V={}, A={}, corrs=[], tau=0, nodes=[], unavail=[], anomaly={}, links={},
                  strength={}, strengthmap=[]):
         """`data`: de-trended (zero-mean) series, (x, y, t) or (lat, lon, t) -- ComplexNetworks.py:12-29."""
@@ -44,7 +48,9 @@ class Network:
             require_cuda()
             data = np.ascontiguousarray(self.data, dtype=np.float64)
             n_upper = int((~np.isnan(data).all(axis=2)).sum())
-            self._eng = NetworkBatch(self.dimX, self.dimY, self.dimT, 1, latlon=False, n_upper=n_upper)
+            ldn = max(128, (n_upper + 127) // 128 * 128)
+            self._eng = NetworkBatch(self.dimX, self.dimY, self.dimT, 1, latlon=False, n_upper=n_upper,
+                                     keep_R=8 * ldn * ldn <= self.max_matrix_bytes)
             self._fields = h2d(data.reshape(1, self.dimX * self.dimY, self.dimT))
             self._job_field = torch.zeros(1, dtype=torch.int32, device="cuda")
             self._job_T = torch.full((1,), self.dimT, dtype=torch.int32, device="cuda")
@@ -55,7 +61,7 @@ class Network:
         eng = self._engine()
         eng.detrend_zscore(self._fields, self._job_field, self._job_T, do_detrend=False)
         rc = torch.tensor([r_crit_ttest(self.dimT, float(significance))], dtype=torch.float64, device="cuda")
-        eng.corr_tau(rc, store_R=True)
+        eng.corr_tau(rc, store_R=eng.R is not None)
         N = int(eng.n_nodes.cpu()[0])
         if int(eng.status.cpu()[0]) == _lib.SIE_JOB_CAPACITY:
             raise _lib.SieError("node capacity exceeded")
@@ -66,7 +72,24 @@ class Network:
 
     def correlation_matrix(self):
         """Dense N x N correlation matrix with NaN diagonal (the reference's `R` before the scatter)."""
+        if self._eng.R is None:
+            return self.correlation_rows(np.arange(self._N))
         return self._eng.R[0, :self._N, :self._N].cpu().numpy()
+
+    def correlation_rows(self, rows):
+        """Rows `rows` of the correlation matrix, (len(rows), N): read from the stored matrix, or recomputed from the
+        unit-norm rows on the device (sie_corr_rows) when the matrix is not kept."""
+        rows = np.atleast_1d(np.asarray(rows, dtype=np.int64))
+        eng, N = self._eng, self._N
+        if eng.R is not None:
+            return eng.R[0, torch.from_numpy(rows).cuda(), :N].cpu().numpy()
+        out = torch.empty((len(rows), N), dtype=torch.float64, device="cuda")
+        for r0 in range(0, len(rows), 32768):
+            part = torch.from_numpy(rows[r0:r0 + 32768].astype(np.int32)).cuda()
+            rc = eng.lib.sie_corr_rows(eng.z[0].data_ptr(), part.data_ptr(), len(part), N, self.dimT, eng.Tp,
+                                       out[r0:].data_ptr(), N, torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "sie_corr_rows")
+        return out.cpu().numpy()
 
     # -- ComplexNetworks.py:49-278 ------------------------------------------------------------------
     def area_level(self, latlon_grid=False):
@@ -128,6 +151,18 @@ class _LazyCorrs:
         return a if dtype is None else a.astype(dtype)
 
     def __getitem__(self, idx):
+        if self._arr is None and self._net._eng.R is None:
+            # no stored matrix (large grid): serve the requested node rows without materialising N x dimX x dimY
+            first, rest = (idx[0], idx[1:]) if isinstance(idx, tuple) else (idx, ())
+            rows = np.arange(self._N)[first]
+            net = self._net
+            R = net.correlation_rows(rows)
+            full = np.full((R.shape[0], net.dimX * net.dimY), np.nan)
+            full[:, net.nodes[0]] = R
+            full = full.reshape((R.shape[0], net.dimX, net.dimY))
+            if np.ndim(rows) == 0:
+                full = full[0]
+            return full[rest] if rest else full
         return self._materialise()[idx]
 
     def __len__(self):

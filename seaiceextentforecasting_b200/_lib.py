@@ -40,9 +40,11 @@ _SIGS = {
     "sie_corr_tau": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, c_p, c_p, c_sz, c_p, c_p, c_p,
                                C.c_int, C.c_int, C.c_int, c_p]),
     "sie_corr_tau_scratch_bytes": (c_sz, [C.c_int, C.c_int]),
-    "sie_corr_stencil": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p]),
-    "sie_area_level": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                 C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p, c_p]),
+    "sie_corr_rows": (C.c_int, [c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, c_p, C.c_int, c_p]),
+    "sie_corr_stencil": (C.c_int, [c_p, c_p, c_p, C.c_int, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   c_p, c_p]),
+    "sie_area_level": (C.c_int, [c_p, c_p, c_p, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_sz, c_p, c_p]),
     "sie_area_level_scratch_bytes": (c_sz, [C.c_int, C.c_int]),
     "sie_intra_links": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p,
                                   c_p, c_p, c_p]),

@@ -186,9 +186,27 @@ __device__ __forceinline__ Rec block_arg(const Rec& v, RecSlot* slots, int& par)
   return warp_arg<PW>(t);
 }
 
-template <class CFG, bool ONCHIP>
+// Correlation of nodes a and c recomputed from their unit-norm rows (R not stored: `ZR` instantiations): the same
+// dot product the correlation kernel accumulates (sequential in k), clipped, NaN on the diagonal.
+__device__ __noinline__ double sie_zcorr(const double* __restrict__ za, const double* __restrict__ zc, int kT, bool diag) {
+  if (diag) return sie_nan();
+  double acc = 0.0;
+  for (int k = 0; k < kT; k += 4) {
+    const double2 a0 = *reinterpret_cast<const double2*>(za + k), a1 = *reinterpret_cast<const double2*>(za + k + 2);
+    const double2 c0 = *reinterpret_cast<const double2*>(zc + k), c1 = *reinterpret_cast<const double2*>(zc + k + 2);
+    acc = fma(a0.x, c0.x, acc);
+    acc = fma(a0.y, c0.y, acc);
+    acc = fma(a1.x, c1.x, acc);
+    acc = fma(a1.y, c1.y, acc);
+  }
+  if (!(fabs(acc) <= 1.0)) acc = acc > 1.0 ? 1.0 : (acc < -1.0 ? -1.0 : acc);   // np.clip keeps NaN
+  return acc;
+}
+
+template <class CFG, bool ONCHIP, bool ZR>
 __global__ void __launch_bounds__(CFG::NT, CFG::CTAS)
-k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil_all,
+k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T, int Tp,
+             const double* __restrict__ stencil_all,
              const int32_t* __restrict__ node_cell_all, const int32_t* __restrict__ cell_node_all,
              const int32_t* __restrict__ n_nodes, const double* __restrict__ tau_all,
              const int32_t* __restrict__ first_nan_cell, int B, int X, int Y, int ldn, int latlon, int MA,
@@ -286,7 +304,15 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   unsigned long long bph[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // bookkeeping-warp phase cycles (its lane 0), work[16..23]
   const int N = min(n_nodes[b], ldn);
   const double tau = tau_all[b];
-  const double* R = Rall + (size_t)b * ldn * ldn;
+  // ZR: `Rall` holds the unit-norm rows z [B][ldn][Tp] and every correlation is recomputed from them
+  const double* R = ZR ? Rall + (size_t)b * ldn * Tp : Rall + (size_t)b * ldn * ldn;
+  const int kT = ZR ? ((job_T[b] + 3) & ~3) : 0;
+  struct RowH { const double* p; int n; };
+  auto rrow = [&](int a) -> RowH { RowH h; h.n = a; h.p = R + (size_t)a * (ZR ? Tp : ldn); return h; };
+  auto rat = [&](const RowH& h, int c) -> double {
+    if constexpr (ZR) return sie_zcorr(h.p, R + (size_t)c * Tp, kT, h.n == c);
+    else return __ldg(h.p + c);
+  };
   const double* sten = stencil_all + (size_t)b * ldn * 4;
   const int32_t* cnode_g = cell_node_all + (size_t)b * C;
   int32_t* out_cells = area_cells_all + (size_t)b * C;
@@ -309,11 +335,11 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   // group: lane j builds numpy's accumulator j = a[j] + a[8+j] + ... over the full groups of 8, keeps tail element
   // j, and the group assembles the pairwise sum in numpy's order.  All gathers are issued before the first add.
   auto init_slot = [&](int s, int fnode, int n) {
-    const double* row = R + (size_t)fnode * ldn;
+    const RowH row = rrow(fnode);
     const int ngrp = n >> 3, nt = n & 7;
     double r, tv;
     int nanc = 0;
-    sie_pw_lane8_any([&](int i) { return __ldg(row + hn[i]); }, 0, n, ngrp, nt, j, r, tv, nanc);
+    sie_pw_lane8_any([&](int i) { return rat(row, hn[i]); }, 0, n, ngrp, nt, j, r, tv, nanc);
     facc[j * FCAP + s] = r;
     ftail[j * FCAP + s] = tv;
     double res = 0.0;
@@ -472,9 +498,9 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
         for (int q = g; q < nf; q += NG) {
           const int f = flist[q];
           if (f < 0) continue;
-          const double* row = R + (size_t)cnode[f] * ldn;
+          const RowH row = rrow(cnode[f]);
           int nanc = 0;
-          const double sum = sie_pw_sum8<MAXD>([&](int i) { return __ldg(row + hn[i]); }, n, j, gmask, nanc);
+          const double sum = sie_pw_sum8<MAXD>([&](int i) { return rat(row, hn[i]); }, n, j, gmask, nanc);
           if (j == 0) wk += (unsigned long long)n;
           nanc += __shfl_xor_sync(gmask, nanc, 1);
           nanc += __shfl_xor_sync(gmask, nanc, 2);
@@ -499,7 +525,7 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
       double v = 0.0;
       if (fast_upd && tid < nf && tid != widx) {
         const int rn = srow[tid];
-        if (rn >= 0) { own = true; v = __ldg(R + (size_t)rn * ldn + mnode); }
+        if (rn >= 0) { own = true; v = rat(rrow(rn), mnode); }
       }
       // --- bookkeeping warp: membership, frontier keys, new frontier cells and their slot state
       if (warp == BKW) {
@@ -585,14 +611,14 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
     d_ok = (to <= dcap) && (from == 0 || d_ok);
     if (!d_ok) return;
     for (int p = g; p < to - 1; p += NG) {
-      const double* row = R + (size_t)hn[p] * ldn;
+      const RowH row = rrow(hn[p]);
       double* drow = D + (size_t)p * ld;
       for (int q0 = max(from, p + 1); q0 < to; q0 += 64) {   // 8 gathers in flight per lane
         double v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int q = min(q0 + 8 * u + j, to - 1);
-          v[u] = __ldg(row + hn[q]);
+          v[u] = rat(row, hn[q]);
         }
         sie_fence_regs<8>(v);
 #pragma unroll
@@ -733,12 +759,12 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
           const int p = sh_r0[qc] + (u - sh_goff[qc]);
           const int nk = sh_koff[qc + 1] - sh_koff[qc];
           const IT* kn = knl + sh_koff[qc];
-          const double* row = R + (size_t)hn[p] * ldn;
+          const RowH row = rrow(hn[p]);
           double* dst = D + (size_t)p * ld + sh_xo[qc];
           for (int qq = 0; qq < nk; qq += 64) {
             double v[8];
 #pragma unroll
-            for (int u2 = 0; u2 < 8; ++u2) v[u2] = __ldg(row + kn[min(qq + 8 * u2 + j, nk - 1)]);
+            for (int u2 = 0; u2 < 8; ++u2) v[u2] = rat(row, kn[min(qq + 8 * u2 + j, nk - 1)]);
             sie_fence_regs<8>(v);
 #pragma unroll
             for (int u2 = 0; u2 < 8; ++u2) { const int q = qq + 8 * u2 + j; if (q < nk) dst[q] = v[u2]; }
@@ -757,9 +783,9 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
           int nanc = 0;
           double sum = 0.0;
           if (len > 0) {
-            const double* row = R + (size_t)kn[pp] * ldn;
+            const RowH row = rrow(kn[pp]);
             const IT* kq = kn + pp + 1;
-            sum = sie_pw_sum8<MAXD>([&](int i) { return __ldg(row + kq[i]); }, len, j, gmask, nanc);
+            sum = sie_pw_sum8<MAXD>([&](int i) { return rat(row, kq[i]); }, len, j, gmask, nanc);
             nanc += __shfl_xor_sync(gmask, nanc, 1);
             nanc += __shfl_xor_sync(gmask, nanc, 2);
             nanc += __shfl_xor_sync(gmask, nanc, 4);
@@ -826,13 +852,13 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
           double sum = 0.0;
           if (len > 0) {
             if (p < nb) {
-              const double* row = R + (size_t)hn[p] * ldn;
+              const RowH row = rrow(hn[p]);
               const int nbb = nb - 1 - p;              // elements of the row inside the best area
-              sum = sie_pw_sum8<MAXD>([&](int i) { const IT* q = (i < nbb) ? hn + (p + 1 + i) : kn + max(i - nbb, 0); return __ldg(row + *q); }, len, j, gmask, nanc);
+              sum = sie_pw_sum8<MAXD>([&](int i) { const IT* q = (i < nbb) ? hn + (p + 1 + i) : kn + max(i - nbb, 0); return rat(row, *q); }, len, j, gmask, nanc);
             } else {
-              const double* row = R + (size_t)kn[p - nb] * ldn;
+              const RowH row = rrow(kn[p - nb]);
               const IT* kq = kn + (p - nb) + 1;
-              sum = sie_pw_sum8<MAXD>([&](int i) { return __ldg(row + kq[i]); }, len, j, gmask, nanc);
+              sum = sie_pw_sum8<MAXD>([&](int i) { return rat(row, kq[i]); }, len, j, gmask, nanc);
             }
             nanc += __shfl_xor_sync(gmask, nanc, 1);
             nanc += __shfl_xor_sync(gmask, nanc, 2);
@@ -960,16 +986,16 @@ k_area_level(const double* __restrict__ Rall, const double* __restrict__ stencil
   }   // persistent loop over the job queue
 }
 
-template <class CFG, bool ONCHIP>
+template <class CFG, bool ONCHIP, bool ZR>
 int launch_area(const SieDevice* dev, int slot, int grid, size_t smem, cudaStream_t st, const double* R,
-                const double* stencil, const int32_t* node_cell, const int32_t* cell_node, const int32_t* n_nodes,
+                const int32_t* job_T, int Tp, const double* stencil, const int32_t* node_cell, const int32_t* cell_node, const int32_t* n_nodes,
                 const double* tau, const int32_t* first_nan_cell, int B, int X, int Y, int ldn, int latlon,
                 int max_areas, int32_t* area_cells, int32_t* area_start, int32_t* area_key, int32_t* n_areas,
                 int32_t* label, int32_t* status, int* queue, unsigned char* scratch, size_t per_cta, int place,
                 unsigned long long* work) {
-  auto kern = k_area_level<CFG, ONCHIP>;
+  auto kern = k_area_level<CFG, ONCHIP, ZR>;
   if (int rc = sie_ensure_smem(dev, slot, (const void*)kern, smem)) return rc;
-  kern<<<grid, CFG::NT, smem, st>>>(R, stencil, node_cell, cell_node, n_nodes, tau, first_nan_cell, B, X, Y, ldn, latlon,
+  kern<<<grid, CFG::NT, smem, st>>>(R, job_T, Tp, stencil, node_cell, cell_node, n_nodes, tau, first_nan_cell, B, X, Y, ldn, latlon,
                                     max_areas, area_cells, area_start, area_key, n_areas, label, status, queue, scratch,
                                     per_cta, place, work);
   return SIE_OK;
@@ -977,10 +1003,10 @@ int launch_area(const SieDevice* dev, int slot, int grid, size_t smem, cudaStrea
 
 // persistent grid: CTAs per SM of the variant this (grid, capacity) selects, and its dynamic shared memory
 struct AreaPlan { int variant, ctas_per_sm, place; size_t smem; };   // variant 0: <256,i16>, 1: <512,i16>, 2: <512,i32>
-AreaPlan plan_area(const SieDevice* dev, int B, int C, int ldn, int max_areas) {
+AreaPlan plan_area(const SieDevice* dev, int B, int C, int ldn, int max_areas, bool force32 = false) {
   AreaPlan pl = {2, 1, 0, 0};
   const size_t budget = (size_t)dev->max_smem_optin - 4096;    // static shared memory + alignment slack
-  if (C < 8192 && ldn <= 32767 && max_areas <= 32766) {
+  if (!force32 && C < 8192 && ldn <= 32767 && max_areas <= 32766) {
     const size_t i16 = 7 * align_up(sizeof(int16_t) * (size_t)C, 16) + area_tab_bytes(max_areas, sizeof(int16_t)) + 64;
     const size_t s256 = align_up(slot_bytes(AreaCfg<256, int16_t>::FCAP), 16) + i16;
     const size_t s512 = align_up(slot_bytes(AreaCfg<512, int16_t>::FCAP), 16) + i16;
@@ -1016,21 +1042,23 @@ extern "C" size_t sie_area_level_scratch_bytes(int B, int C) {
   return QUEUE_BYTES + (size_t)g * scratch_per_cta(C, C / 2 + 1);
 }
 
-extern "C" int sie_area_level(const double* R, const double* stencil, const int32_t* node_cell,
-                              const int32_t* cell_node, const int32_t* n_nodes, const double* tau,
-                              const int32_t* first_nan_cell, int B, int X, int Y, int ldn, int latlon,
+extern "C" int sie_area_level(const double* R, const double* z, const int32_t* job_T, int Tp, const double* stencil,
+                              const int32_t* node_cell, const int32_t* cell_node, const int32_t* n_nodes,
+                              const double* tau, const int32_t* first_nan_cell, int B, int X, int Y, int ldn, int latlon,
                               int max_areas, int32_t* area_cells, int32_t* area_start, int32_t* area_key,
                               int32_t* n_areas, int32_t* label, int32_t* status, void* scratch,
                               size_t scratch_bytes, uint64_t* work, void* stream) {
-  SIE_CHECK_ARG(R && stencil && node_cell && cell_node && n_nodes && tau && first_nan_cell && area_cells &&
+  SIE_CHECK_ARG(stencil && node_cell && cell_node && n_nodes && tau && first_nan_cell && area_cells &&
                     area_start && area_key && n_areas && label && status && scratch, "null pointer");
+  SIE_CHECK_ARG(R || (z && job_T && Tp >= 4 && (Tp % 4) == 0), "without R the unit-norm rows z, job_T and Tp are needed");
   SIE_CHECK_ARG(B > 0 && X > 0 && Y > 0 && ldn > 0 && max_areas > 0, "non-positive size");
   const int C = X * Y;
   SIE_CHECK_ARG(max_areas <= C / 2 + 1, "max_areas cannot exceed C/2+1");
   SIE_CHECK_ARG((long long)C < (1ll << 22), "grid too large (frontier key encoding / pairwise tree depth)");
   const SieDevice* dev = sie_device();
   if (!dev) return SIE_ERR_LAUNCH;
-  const AreaPlan pl = plan_area(dev, B, C, ldn, max_areas);
+  const bool zr = (R == nullptr);      // correlations recomputed from z (the matrix is never materialised)
+  const AreaPlan pl = plan_area(dev, B, C, ldn, max_areas, zr);
   SIE_CHECK_ARG(pl.smem <= (size_t)dev->max_smem_optin - 4096, "shared memory budget");
   const size_t per_cta = scratch_per_cta(C, max_areas);
   SIE_CHECK_ARG(scratch_bytes >= QUEUE_BYTES + per_cta, "scratch too small");
@@ -1044,16 +1072,21 @@ extern "C" int sie_area_level(const double* R, const double* stencil, const int3
   if (cudaMemsetAsync(queue, 0, sizeof(int), st) != cudaSuccess) SIE_CHECK_LAUNCH();
   int rc;
 #define SIE_AREA_ARGS                                                                                                   \
-  R, stencil, node_cell, cell_node, n_nodes, tau, first_nan_cell, B, X, Y, ldn, latlon, max_areas, area_cells, area_start, \
-      area_key, n_areas, label, status, queue, blocks, per_cta, pl.place, (unsigned long long*)work
-  if (pl.variant == 0)
-    rc = launch_area<AreaCfg<256, int16_t>, true>(dev, SIE_K_AREA_ON16_2, (int)grid, pl.smem, st, SIE_AREA_ARGS);
+  job_T, Tp, stencil, node_cell, cell_node, n_nodes, tau, first_nan_cell, B, X, Y, ldn, latlon, max_areas, area_cells,   \
+      area_start, area_key, n_areas, label, status, queue, blocks, per_cta, pl.place, (unsigned long long*)work
+  const bool on32 = (pl.place == 0 && C < 8192);
+  if (zr && on32)
+    rc = launch_area<AreaCfg<512, int32_t>, true, true>(dev, SIE_K_AREA_ON32_Z, (int)grid, pl.smem, st, z, SIE_AREA_ARGS);
+  else if (zr)
+    rc = launch_area<AreaCfg<512, int32_t>, false, true>(dev, SIE_K_AREA_OFF32_Z, (int)grid, pl.smem, st, z, SIE_AREA_ARGS);
+  else if (pl.variant == 0)
+    rc = launch_area<AreaCfg<256, int16_t>, true, false>(dev, SIE_K_AREA_ON16_2, (int)grid, pl.smem, st, R, SIE_AREA_ARGS);
   else if (pl.variant == 1)
-    rc = launch_area<AreaCfg<512, int16_t>, true>(dev, SIE_K_AREA_ON16, (int)grid, pl.smem, st, SIE_AREA_ARGS);
-  else if (pl.place == 0 && C < 8192)
-    rc = launch_area<AreaCfg<512, int32_t>, true>(dev, SIE_K_AREA_ON32, (int)grid, pl.smem, st, SIE_AREA_ARGS);
+    rc = launch_area<AreaCfg<512, int16_t>, true, false>(dev, SIE_K_AREA_ON16, (int)grid, pl.smem, st, R, SIE_AREA_ARGS);
+  else if (on32)
+    rc = launch_area<AreaCfg<512, int32_t>, true, false>(dev, SIE_K_AREA_ON32, (int)grid, pl.smem, st, R, SIE_AREA_ARGS);
   else
-    rc = launch_area<AreaCfg<512, int32_t>, false>(dev, SIE_K_AREA_OFF32, (int)grid, pl.smem, st, SIE_AREA_ARGS);
+    rc = launch_area<AreaCfg<512, int32_t>, false, false>(dev, SIE_K_AREA_OFF32, (int)grid, pl.smem, st, R, SIE_AREA_ARGS);
 #undef SIE_AREA_ARGS
   if (rc) return rc;
   SIE_CHECK_LAUNCH();

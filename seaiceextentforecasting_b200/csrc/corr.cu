@@ -663,8 +663,10 @@ k_tau_finalize(const double* __restrict__ tile_pair, const long long* __restrict
   }
 }
 
-// K3: one thread per (node, direction)
-__global__ void k_stencil(const double* __restrict__ R, const int32_t* __restrict__ node_cell,
+// K3: one thread per (node, direction).  R == nullptr: the correlation is recomputed from the two unit-norm rows
+// (sequential in k like the tensor-core accumulation, clipped), so the seed search works without a stored matrix.
+__global__ void k_stencil(const double* __restrict__ R, const double* __restrict__ z,
+                          const int32_t* __restrict__ job_T, int Tp, const int32_t* __restrict__ node_cell,
                           const int32_t* __restrict__ cell_node, const int32_t* __restrict__ n_nodes, int B,
                           int X, int Y, int ldn, int latlon, double* __restrict__ stencil) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -684,13 +686,54 @@ __global__ void k_stencil(const double* __restrict__ R, const int32_t* __restric
     if (q >= Y) { if (latlon) q = 0; else ok = false; }
     if (ok) {
       const int m = cell_node[(size_t)b * X * Y + a * Y + q];
-      if (m >= 0 && m < N) out = R[(size_t)b * ldn * ldn + (size_t)n * ldn + m];
+      if (m >= 0 && m < N) {
+        if (R) {
+          out = R[(size_t)b * ldn * ldn + (size_t)n * ldn + m];
+        } else {
+          const double* za = z + ((size_t)b * ldn + n) * Tp;
+          const double* zc = z + ((size_t)b * ldn + m) * Tp;
+          const int kT = (job_T[b] + 3) & ~3;
+          double acc = 0.0;
+          for (int k = 0; k < kT; ++k) acc = fma(za[k], zc[k], acc);
+          out = clip_unit(acc);
+          if (m == n) out = sie_nan();
+        }
+      }
     }
   }
   stencil[idx] = out;
 }
 
+// selected rows of R recomputed from z: one thread per (row, column); the same sequential dot product as K3 / K4
+__global__ void k_corr_rows_from_z(const double* __restrict__ z, const int32_t* __restrict__ rows, int n_rows, int N,
+                                   int T, int Tp, double* __restrict__ out, int ld_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= N || r >= n_rows) return;
+  const int a = rows[r];
+  double v = sie_nan();
+  if (a >= 0 && a < N && a != c) {
+    const double* za = z + (size_t)a * Tp;
+    const double* zc = z + (size_t)c * Tp;
+    const int kT = (T + 3) & ~3;
+    double acc = 0.0;
+    for (int k = 0; k < kT; ++k) acc = fma(za[k], zc[k], acc);
+    v = clip_unit(acc);
+  }
+  out[(size_t)r * ld_out + c] = v;
+}
+
 }  // namespace
+
+extern "C" int sie_corr_rows(const double* z, const int32_t* rows, int n_rows, int N, int T, int Tp, double* out,
+                             int ld_out, void* stream) {
+  SIE_CHECK_ARG(z && rows && out, "null pointer");
+  SIE_CHECK_ARG(n_rows > 0 && n_rows <= 65535 && N > 0 && T > 0 && Tp >= T && ld_out >= N, "bad size");
+  k_corr_rows_from_z<<<dim3((unsigned)((N + 255) / 256), (unsigned)n_rows), 256, 0, (cudaStream_t)stream>>>(
+      z, rows, n_rows, N, T, Tp, out, ld_out);
+  SIE_CHECK_LAUNCH();
+  return SIE_OK;
+}
 
 extern "C" size_t sie_corr_tau_scratch_bytes(int B, int ldn) {
   long long nb = (ldn + TILE - 1) / TILE;
@@ -773,14 +816,16 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
   return SIE_OK;
 }
 
-extern "C" int sie_corr_stencil(const double* R, const int32_t* node_cell, const int32_t* cell_node,
+extern "C" int sie_corr_stencil(const double* R, const double* z, const int32_t* job_T, int Tp,
+                                const int32_t* node_cell, const int32_t* cell_node,
                                 const int32_t* n_nodes, int B, int X, int Y, int ldn, int latlon,
                                 double* stencil, void* stream) {
-  SIE_CHECK_ARG(R && node_cell && cell_node && n_nodes && stencil, "null pointer");
+  SIE_CHECK_ARG(node_cell && cell_node && n_nodes && stencil, "null pointer");
+  SIE_CHECK_ARG(R || (z && job_T && Tp > 0), "without R the unit-norm rows z, job_T and Tp are needed");
   SIE_CHECK_ARG(B > 0 && X > 0 && Y > 0 && ldn > 0, "non-positive size");
   const long long total = (long long)B * ldn * 4;
-  k_stencil<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(R, node_cell, cell_node, n_nodes,
-                                                                               B, X, Y, ldn, latlon, stencil);
+  k_stencil<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(R, z, job_T, Tp, node_cell, cell_node,
+                                                                               n_nodes, B, X, Y, ldn, latlon, stencil);
   SIE_CHECK_LAUNCH();
   return SIE_OK;
 }

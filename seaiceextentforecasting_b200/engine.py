@@ -159,10 +159,12 @@ class NetworkBatch:
         self.launches += 5
 
     def area_level(self, jr=None):
-        """K3 + K4/K5."""
+        """K3 + K4/K5.  Without a stored matrix (keep_R=False) every correlation is recomputed from the z rows."""
         j0, j1 = self._range(jr)
         n = j1 - j0
-        rc = self.lib.sie_corr_stencil(_ptr(self.R[j0:]), _ptr(self.node_cell[j0:]), _ptr(self.cell_node[j0:]),
+        R = _ptr(self.R[j0:]) if self.R is not None else C.c_void_p(0)
+        rc = self.lib.sie_corr_stencil(R, _ptr(self.z[j0:]), _ptr(self.job_T[j0:]), self.Tp,
+                                       _ptr(self.node_cell[j0:]), _ptr(self.cell_node[j0:]),
                                        _ptr(self.n_nodes[j0:]), n, self.X, self.Y, self.ldn, int(self.latlon),
                                        _ptr(self.stencil[j0:]), _stream())
         _lib.check(rc, "sie_corr_stencil")
@@ -170,7 +172,8 @@ class NetworkBatch:
         if scratch is None:
             nbytes = int(self.lib.sie_area_level_scratch_bytes(n, self.C))
             scratch = self._area_scratch[(j0, j1)] = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device="cuda")
-        rc = self.lib.sie_area_level(_ptr(self.R[j0:]), _ptr(self.stencil[j0:]), _ptr(self.node_cell[j0:]),
+        rc = self.lib.sie_area_level(R, _ptr(self.z[j0:]), _ptr(self.job_T[j0:]), self.Tp,
+                                     _ptr(self.stencil[j0:]), _ptr(self.node_cell[j0:]),
                                      _ptr(self.cell_node[j0:]), _ptr(self.n_nodes[j0:]), _ptr(self.tau[j0:]),
                                      _ptr(self.first_nan[j0:]), n, self.X, self.Y, self.ldn, int(self.latlon),
                                      self.MA, _ptr(self.area_cells[j0:]), _ptr(self.area_start[j0:]),
@@ -200,7 +203,7 @@ class NetworkBatch:
 
     def build(self, fields, job_field, job_T, r_crit, scale, do_detrend=True, jr=None):
         self.detrend_zscore(fields, job_field, job_T, do_detrend, jr)
-        self.corr_tau(r_crit, jr=jr)
+        self.corr_tau(r_crit, store_R=self.R is not None, jr=jr)
         self.area_level(jr)
         self.intra_links(scale, jr)
 

@@ -214,6 +214,53 @@ def mlii(theta, y, anoms_sic, anoms_sst=None, rule=0, alpha=0.05, zscore=False):
     return np.float64(r["nlml"]), np.asarray([r["g_ell"], r["g_sig"]])
 
 
+class MliiObjective:
+    """`MLII(hyperparameters)` of one forecast problem as a callable for an optimiser: the node series and targets are
+    uploaded once, every call evaluates the negative log marginal likelihood and its gradient on the device."""
+
+    def __init__(self, y, anoms_sic, anoms_sst=None, rule=0, alpha=0.05, zscore=False):
+        require_cuda()
+        y = np.asarray(y, dtype=np.float64).reshape(-1)
+        n = y.size
+        self.s1 = _SeriesSet(anoms_sic, n)
+        self.s2 = _SeriesSet(anoms_sst, n) if anoms_sst is not None else None
+        self.prob = _one_problem(n, anoms_sst, rule, alpha, zscore, True)
+        self.y = h2d(y)
+        npred = self.s1.MA + (self.s2.MA if self.s2 is not None else 0)
+        self.gp = GpBatch(1, max_pred=max(4, npred))
+        self.evaluations = 0
+
+    def record(self, theta):
+        self.prob["ell"] = float(np.exp(theta[0]))
+        self.prob["sig"] = float(np.exp(theta[1]))
+        self.gp.run(h2d(self.prob.view(np.uint8)), self.y, self.s1, self.s2)
+        self.evaluations += 1
+        return self.gp.results()[0]
+
+    def __call__(self, theta):
+        r = self.record(theta)
+        if r["info"] != 0 or not np.isfinite(r["nlml"]):
+            return np.inf, np.asarray([np.inf, np.inf])            # the `except` branch of MLII, north/June1st.py:254-256
+        return float(r["nlml"]), np.asarray([r["g_ell"], r["g_sig"]], dtype=np.float64)
+
+
+def optimise_hyperparameters(y, anoms_sic, anoms_sst=None, rule=0, alpha=0.05, zscore=False, ell0=None, sig0=None,
+                             from_grid=False):
+    """The hyper-parameter optimisation the reference leaves commented out (north/June1st.py:259-262):
+        theta = minimize(MLII, x0=[log(l_init), log(sigma_init)], method='CG', jac=True, options={'disp': False}).x
+    with MLII and its gradient evaluated on the device.  `from_grid`: start from the minimum of the 20 x 20
+    (l, sigma_n~) grid of :210-211 instead of (ell0, sig0).  Returns (l, sigma_n~, scipy OptimizeResult)."""
+    from scipy.optimize import minimize
+    if from_grid:
+        ells, sigs = np.logspace(-7, 2, 20), np.logspace(-3, 9, 20)
+        _, (i, j) = hyper_grid(y, anoms_sic, anoms_sst, rule, alpha, zscore, ells, sigs)
+        ell0, sig0 = ells[i], sigs[j]
+    obj = MliiObjective(y, anoms_sic, anoms_sst, rule, alpha, zscore)
+    res = minimize(obj, x0=[np.log(ell0), np.log(sig0)], method="CG", jac=True, options={"disp": False})
+    res.evaluations = obj.evaluations
+    return float(np.exp(res.x[0])), float(np.exp(res.x[1])), res
+
+
 # ------------------------------------------------------------------------------------------------
 # retrospective sweep
 # ------------------------------------------------------------------------------------------------
@@ -380,7 +427,7 @@ class RetrospectiveSweep:
     """
 
     def __init__(self, config_names, sic_fields, sie, fmin, fmax, psar, sst_field=None, sst_lat=None,
-                 significance=0.01, max_areas=None, max_pred=384, rank=0, world=1, wave_T=(12,)):
+                 significance=0.01, max_areas=None, max_pred=384, rank=0, world=1, wave_T=(12,), keep_R=True):
         require_cuda()
         member_fields = list(sic_fields) if isinstance(sic_fields, (list, tuple)) else [sic_fields]
         self.members = len(member_fields)
@@ -398,8 +445,10 @@ class RetrospectiveSweep:
         # is a node of the early windows
         Tmin = int(plan.job_T.min()) if len(plan.job_T) else self.Tfull
         n_upper = int(max((~np.isnan(f[:, :Tmin]).any(axis=1)).sum() for f in self.sic_host))
+        # keep_R=False: the correlation matrices are never stored (tau-only K2); domain growth recomputes every
+        # correlation it consumes from the unit-norm rows -- for grids whose N x N matrices do not fit in HBM
         self.sic = NetworkBatch(self.X, self.Y, self.Tfull, max(1, len(plan.jobs)), latlon=False, n_upper=n_upper,
-                                max_areas=max_areas)
+                                max_areas=max_areas, keep_R=keep_R)
         self.sst = None
         if self.use_sst:
             sst_members = list(sst_field) if isinstance(sst_field, (list, tuple)) else [sst_field] * self.members
@@ -411,7 +460,7 @@ class RetrospectiveSweep:
             Tmin_s = int(plan.sst_T.min())
             n_up = int(max((~np.isnan(f[:, :Tmin_s]).any(axis=1)).sum() for f in self.sst_host))
             self.sst = NetworkBatch(self.Xs, self.Ys, self.Tfull, len(plan.sst_years), latlon=True, n_upper=n_up,
-                                    max_areas=max_areas)
+                                    max_areas=max_areas, keep_R=keep_R)
         self.P = plan.P
         self.n_forecasts = plan.P
         self.gp = GpBatch(max(1, self.P), max_pred=max_pred)
@@ -529,7 +578,7 @@ class RetrospectiveSweep:
             mark(tag + ".start")
             eng.detrend_zscore(fields, job_field, job_T, do_detrend=True, jr=jr)
             mark(tag + ".detrend_zscore")
-            eng.corr_tau(rcrit, jr=jr)
+            eng.corr_tau(rcrit, store_R=eng.R is not None, jr=jr)
             mark(tag + ".corr_tau")
             eng.area_level(jr=jr)
             mark(tag + ".area_level")

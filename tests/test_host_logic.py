@@ -110,6 +110,29 @@ def _worker(rank, world, port, q):
                 for k, reg in enumerate(cfg.regions):
                     exp = np.array([m * 10000 + ci * 1000 + k * 100 + (y - 2000) for y in plan.years], dtype=float)
                     ok &= np.array_equal(o[cfg.name][reg + "_raw_fmean"], exp)
+    # labels / node-series collectives (parallel.all_gather_networks, broadcast_networks) on CPU tensors
+    import torch
+    n_total, C, MA, T = 5, 12, 4, 6                                  # 5 networks over 2 ranks: rank 0 owns 0,2,4, rank 1 owns 1,3
+
+    def fake_state(jobs):
+        st = {}
+        for k in parallel.NETWORK_TENSORS:
+            shape = {"n_areas": (), "area_key": (MA,), "area_start": (MA + 1,), "area_cells": (C,), "label": (C,),
+                     "status": (), "anomaly": (MA, T)}[k]
+            dt = torch.float64 if k == "anomaly" else torch.int32
+            st[k] = torch.stack([torch.full(shape, float(j * 10 + len(k)), dtype=dt) for j in jobs]) if jobs else \
+                torch.zeros((0,) + shape, dtype=dt)
+        return st
+
+    mine = list(range(rank, n_total, world))
+    full = parallel.all_gather_networks(fake_state(mine), n_total)
+    for k in parallel.NETWORK_TENSORS:
+        for j in range(n_total):
+            ok &= bool((full[k][j] == j * 10 + len(k)).all())
+    st = fake_state([0, 1]) if rank == 1 else {k: torch.zeros_like(v) for k, v in fake_state([0, 1]).items()}
+    parallel.broadcast_networks(st, src=1)
+    ref = fake_state([0, 1])
+    ok &= all(bool(torch.equal(st[k], ref[k])) for k in parallel.NETWORK_TENSORS)
     if rank == 0:
         q.put(bool(ok))
     dist.barrier()

@@ -293,3 +293,41 @@ def test_full_size_25km_correlation_properties(lib_built):
     dtc = eng.dt[0].cpu().numpy()[eng.node_cell[0, :N].cpu().numpy()[np.sort(idx)], :T]
     ref = np.corrcoef(dtc)
     assert np.max(np.abs(Rs - ref)) <= 1e-9                                 # unit-norm rows reproduce np.corrcoef
+
+
+@pytest.mark.parametrize("X,Y,T,latlon,seed", [(20, 20, 42, False, 5), (26, 90, 42, True, 7), (57, 57, 19, False, 109),
+                                               (57, 57, 42, False, 9), (18, 60, 7, True, 105), (81, 81, 12, False, 31)])
+def test_network_without_stored_matrix(lib_built, X, Y, T, latlon, seed):
+    """The no-R path (large grids: `tau` runs the tau-only correlation pass, `area_level` recomputes every correlation it
+    consumes from the unit-norm rows, `corrs[n]` recomputes rows on demand) against the stored-R path and the oracle:
+    nodes, V (keys, membership, order) bit-exact; tau <= 1e-12; node series equal; correlation rows <= 2 ulp."""
+    from seaiceextentforecasting_b200.ComplexNetworks import Network
+    from seaiceextentforecasting_b200.forecast import detrend
+
+    class NoMatrix(Network):
+        max_matrix_bytes = 0
+
+    data, _ = syn.make_field(X, Y, T, seed, latlon=latlon)
+    dt, _ = detrend(data)
+    kw = {"lat": syn.make_lat_grid(X, Y)} if latlon else {"area": syn.make_psar(X, Y)}
+    a = _product(dt, latlon, kw)
+    b = NoMatrix(data=dt)
+    NoMatrix.tau(b, 0.01)
+    assert b._eng.R is None
+    NoMatrix.area_level(b, latlon_grid=latlon)
+    NoMatrix.intra_links(b, **kw)
+    o = _oracle(dt, latlon, kw)
+    assert np.array_equal(a.nodes, b.nodes) and np.array_equal(b.nodes, o.nodes)
+    assert abs(a.tau - b.tau) <= 1e-12 * abs(a.tau) and abs(b.tau - o.tau) <= 1e-9 * abs(o.tau)
+    assert list(b.V.keys()) == list(o.V.keys()) and all(b.V[k] == o.V[k] for k in o.V)      # bit-exact domains
+    assert list(a.V.keys()) == list(b.V.keys()) and all(a.V[k] == b.V[k] for k in a.V)
+    for k in a.V:
+        assert np.array_equal(a.anomaly[k], b.anomaly[k])
+    rows = [0, 1, b.nodes.shape[1] // 2, b.nodes.shape[1] - 1]
+    Ra, Rb = a.correlation_rows(rows), b.correlation_rows(rows)
+    assert np.array_equal(np.isnan(Ra), np.isnan(Rb))
+    m = ~np.isnan(Ra)
+    assert np.abs(Ra[m] - Rb[m]).max() <= 4.5e-16          # tensor-core accumulation vs the sequential FMA chain
+    print(f"{X}x{Y}x{T}: recomputed rows bitwise equal to the stored (DMMA) matrix: {np.array_equal(Ra[m], Rb[m])}")
+    ca, cb = np.asarray(a.corrs[rows[2]]), np.asarray(b.corrs[rows[2]])
+    assert ca.shape == cb.shape == (X, Y) and np.array_equal(np.isnan(ca), np.isnan(cb))
