@@ -73,7 +73,10 @@ int sie_detrend_zscore(const double* fields, const int32_t* job_field, const int
  *     (bitwise symmetric) store, and the significance threshold tau.
  * Replaces: np.corrcoef + fill_diagonal + t-test + mean      ComplexNetworks.py:34-35, :41-47
  * r_crit   [B]  host-computed critical correlation: P<alpha  <=>  R > r_crit
- * R        [B][ldn][ldn] or NULL (tau only; nothing but Z is read and 16 B/tile written)
+ * R        [B][ldn][ldn] or NULL (tau only; nothing but Z is read and 16 B/tile written).  Only the UPPER TRIANGLE is
+ *          defined: R[i][j] for i < j, NaN on the diagonal; element (i, j) is read as R[min(i,j)][max(i,j)] by K3, K4/K5
+ *          and the host accessors, which makes the matrix symmetric by construction and halves the bytes K2 stores
+ *          (SIE_CORR_ROWS also writes the mirror image; do not rely on it)
  * tile_part scratch of sie_corr_tau_scratch_bytes(B, ldn) bytes: tile table (32 B/tile), deterministic per-warp and
  *           per-tile (sum,count) partials; a job range of a batch may use a disjoint slice
  * tau      [B]; tau_sum [B]; tau_cnt [B] (int64)   -- sums are over BOTH triangles like the reference

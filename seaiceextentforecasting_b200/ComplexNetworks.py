@@ -74,15 +74,22 @@ class Network:
         """Dense N x N correlation matrix with NaN diagonal (the reference's `R` before the scatter)."""
         if self._eng.R is None:
             return self.correlation_rows(np.arange(self._N))
-        return self._eng.R[0, :self._N, :self._N].cpu().numpy()
+        U = torch.triu(self._eng.R[0, :self._N, :self._N], diagonal=1)      # only the upper triangle is stored
+        R = (U + U.T).cpu().numpy()
+        np.fill_diagonal(R, np.nan)
+        return R
 
     def correlation_rows(self, rows):
         """Rows `rows` of the correlation matrix, (len(rows), N): read from the stored matrix, or recomputed from the
         unit-norm rows on the device (sie_corr_rows) when the matrix is not kept."""
         rows = np.atleast_1d(np.asarray(rows, dtype=np.int64))
         eng, N = self._eng, self._N
-        if eng.R is not None:
-            return eng.R[0, torch.from_numpy(rows).cuda(), :N].cpu().numpy()
+        if eng.R is not None:                  # element (r, c) lives at R[min(r, c)][max(r, c)]
+            r = torch.from_numpy(rows).cuda()[:, None]
+            c = torch.arange(N, device="cuda")[None, :]
+            out = eng.R[0][torch.minimum(r, c), torch.maximum(r, c)]
+            out[r == c] = float("nan")
+            return out.cpu().numpy()
         out = torch.empty((len(rows), N), dtype=torch.float64, device="cuda")
         for r0 in range(0, len(rows), 32768):
             part = torch.from_numpy(rows[r0:r0 + 32768].astype(np.int32)).cuda()

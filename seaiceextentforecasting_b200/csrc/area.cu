@@ -311,7 +311,7 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
   auto rrow = [&](int a) -> RowH { RowH h; h.n = a; h.p = R + (size_t)a * (ZR ? Tp : ldn); return h; };
   auto rat = [&](const RowH& h, int c) -> double {
     if constexpr (ZR) return sie_zcorr(h.p, R + (size_t)c * Tp, kT, h.n == c);
-    else return __ldg(h.p + c);
+    else return (c >= h.n) ? __ldg(h.p + c) : __ldg(R + (size_t)c * ldn + h.n);   // upper triangle stored: R[min][max]
   };
   const double* sten = stencil_all + (size_t)b * ldn * 4;
   const int32_t* cnode_g = cell_node_all + (size_t)b * C;

@@ -9,10 +9,12 @@
 // UBLKCP, the TMA engine) completing on an mbarrier; Tp = 4 (mod 8) makes the fragment loads
 // bank-conflict free without swizzling.  Persistent 256-thread CTAs (two per SM, so one CTA's stores overlap
 // the other's MMAs) walk a precomputed table of 128x64 tiles on or right of the diagonal blocks; only those
-// tiles are computed and results are mirrored, so R is bitwise symmetric like numpy's syrk-based corrcoef
-// (SURVEY.md H1).  Off-diagonal tiles are staged in shared memory (over the operand panels) and written as
-// whole rows: 512-byte runs for the tile, 1-KB runs for its transpose.
-// Algorithmic work: N(N+1)T flop per network (upper triangle), 8 N^2 bytes if R is stored.
+// tiles are computed, and only the UPPER TRIANGLE of R is stored: every reader (K3, K4/K5, the host accessors)
+// addresses R[min(i,j)][max(i,j)], so the matrix is symmetric by construction like numpy's syrk-based corrcoef
+//  and K2 writes 4 N^2 instead of 8 N^2 bytes.  Off-diagonal tiles are staged in shared memory (over
+// the operand panels) and written as whole rows: 512-byte runs.  (k_corr_rows' stored mode still writes the mirror
+// too; it is a superset of what the readers need.)
+// Algorithmic work: N(N+1)T flop per network (upper triangle), 4 N(N+1) bytes if R is stored.
 #include "common.cuh"
 
 namespace {
@@ -202,10 +204,9 @@ k_corr_tiles(const double* __restrict__ z, const int32_t* __restrict__ n_nodes,
     double lsum = 0.0, lcnt = 0.0;
     double* Rb = R ? R + (size_t)b * ldn * ldn : nullptr;
     if (staged) {
-      // Every element of an off-diagonal tile is above the diagonal: it is written twice, as R[gi][gj] and R[gj][gi].
-      // Stage the clipped tile in shared memory (over the operand panels, once every warp has finished its MMAs) and
-      // write whole rows: 512-byte runs for the tile itself, 1-KB runs for its transpose, instead of 64-byte pieces
-      // scattered over 192 DRAM pages.
+      // Every element of an off-diagonal tile is above the diagonal.  Only the upper triangle of R is stored (readers
+      // address R[min(i,j)][max(i,j)]): stage the clipped tile in shared memory (over the operand panels, once every
+      // warp has finished its MMAs) and write whole rows, 512-byte runs, instead of 64-byte pieces per fragment.
       __syncthreads();                               // all warps done with the panels
       double* Cs = reinterpret_cast<double*>(smem_raw);
 #pragma unroll
@@ -251,31 +252,6 @@ k_corr_tiles(const double* __restrict__ z, const int32_t* __restrict__ n_nodes,
           }
         }
       }
-      // its transpose: column c -> row col0+c of R, 128 doubles, lane l writes columns 2l, 2l+1 and 64+2l, 64+2l+1
-      for (int c0 = warp; c0 < TILE_N; c0 += 2 * NWARP) {
-        double v[2][2][2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int r = 64 * h + 2 * lane, c = c0 + u * NWARP;
-            v[u][h][0] = Cs[r * CS_LD + c];
-            v[u][h][1] = Cs[(r + 1) * CS_LD + c];
-          }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int gj = col0 + c0 + u * NWARP;
-          if (gj < N) {
-            double* dst = Rb + (size_t)gj * ldn + row0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int r = 64 * h + 2 * lane;
-              if (row0 + r + 1 < N) *reinterpret_cast<double2*>(dst + r) = make_double2(v[u][h][0], v[u][h][1]);
-              else if (row0 + r < N) dst[r] = v[u][h][0];
-            }
-          }
-        }
-      }
       __syncthreads();                               // staging buffer free: the next panels may land
       if (tid == 0 && item + gridDim.x < total) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of Cs before the bulk copy lands
@@ -301,17 +277,11 @@ k_corr_tiles(const double* __restrict__ z, const int32_t* __restrict__ n_nodes,
           if (diag_tile) {
             if (in0 && gj == gi) Rb[(size_t)gi * ldn + gj] = sie_nan();
             if (in1 && gj + 1 == gi) Rb[(size_t)gi * ldn + gj + 1] = sie_nan();
-            if (up0) { Rb[(size_t)gi * ldn + gj] = v0; Rb[(size_t)gj * ldn + gi] = v0; }
-            if (up1) { Rb[(size_t)gi * ldn + gj + 1] = v1; Rb[(size_t)(gj + 1) * ldn + gi] = v1; }
+            if (up0) Rb[(size_t)gi * ldn + gj] = v0;
+            if (up1) Rb[(size_t)gi * ldn + gj + 1] = v1;
           } else {
-            if (in1) {
-              *reinterpret_cast<double2*>(Rb + (size_t)gi * ldn + gj) = make_double2(v0, v1);
-              Rb[(size_t)gj * ldn + gi] = v0;
-              Rb[(size_t)(gj + 1) * ldn + gi] = v1;
-            } else if (in0) {
-              Rb[(size_t)gi * ldn + gj] = v0;
-              Rb[(size_t)gj * ldn + gi] = v0;
-            }
+            if (in1) *reinterpret_cast<double2*>(Rb + (size_t)gi * ldn + gj) = make_double2(v0, v1);
+            else if (in0) Rb[(size_t)gi * ldn + gj] = v0;
           }
         }
       }
@@ -688,7 +658,8 @@ __global__ void k_stencil(const double* __restrict__ R, const double* __restrict
       const int m = cell_node[(size_t)b * X * Y + a * Y + q];
       if (m >= 0 && m < N) {
         if (R) {
-          out = R[(size_t)b * ldn * ldn + (size_t)n * ldn + m];
+          out = (m == n) ? sie_nan()
+                         : R[(size_t)b * ldn * ldn + (size_t)min(n, m) * ldn + max(n, m)];   // upper triangle stored
         } else {
           const double* za = z + ((size_t)b * ldn + n) * Tp;
           const double* zc = z + ((size_t)b * ldn + m) * Tp;

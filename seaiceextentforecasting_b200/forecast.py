@@ -545,8 +545,9 @@ class RetrospectiveSweep:
 
     def compute(self, marks=None, waves=None):
         """Enqueue the whole hot path on the current stream (no host sync).  `marks`: optional list that receives
-        (stage name, torch.cuda.Event) pairs recorded after each stage, for per-kernel timing.  `waves`: 1 = one
-        batch per grid (stage timing), 2 = short/long-window waves on separate streams (default when possible).
+        (stage name, torch.cuda.Event) pairs recorded after each stage, for per-kernel timing.  `waves`: 0 = every
+        stage alone on one stream (clean per-stage timing), 1 = one batch per grid with the SST chain on a side stream,
+        2 = short/long-window waves on separate streams (default when possible).
         With `use_graph` (SIE_GRAPH=1) the default call (no marks, default waves) is captured once into a CUDA graph -
         ~55 kernels on up to five streams with their cross-stream dependencies - and replayed afterwards: one launch
         per step instead of ~150 ctypes / stream calls.  Measured on B200 (same box, N = 1 and 2): the replayed step is
@@ -586,6 +587,15 @@ class RetrospectiveSweep:
             mark(tag + ".intra_links")
 
         main = torch.cuda.current_stream()
+        if waves == 0:
+            # fully serial on the current stream (per-stage timing: no other kernel shares the GPU with the timed stage)
+            if self.sst is not None:
+                chain("sst", self.sst, d["sst"], d["sst_field_idx"], d["sst_T"], d["sst_rcrit"], d["lat"])
+            chain("sic", self.sic, d["sic"], d["job_field"], d["job_T"], d["rcrit"], d["psar"])
+            mark("gp.start")
+            self.gp.run(d["prob"], d["y"], self.sic, self.sst)
+            mark("gp")
+            return
         if not two:
             if self.sst is not None:
                 # the SST networks are independent of the SIC ones: run their chain on a side stream so the two

@@ -192,7 +192,7 @@ def test_run_many_equals_run(lib_built):
 def test_full_size_north_sweep_invariants(lib_built):
     """BASELINE.json configs[1] at its full size (the bench workload: 144 SIC 57x57 + 36 SST 26x90 networks, 432
     forecasts; the oracle needs ~10 minutes for it) through size-independent properties: every network builds, areas
-    partition the labelled cells, R is bitwise symmetric with a NaN diagonal, node series are the scaled sums of their
+    partition the labelled cells, the stored upper triangle of R is finite in [-1, 1] with a NaN diagonal, node series are the scaled sums of their
     member cells, every forecast but the known ill-conditioned July/Chukchi configuration is finite with positive variance,
     and a second run reproduces the first bit for bit."""
     import bench
@@ -218,7 +218,8 @@ def test_full_size_north_sweep_invariants(lib_built):
                 assert (lab[b, mem] == a).all() and len(set(mem.tolist())) == len(mem)
         N = int(eng.n_nodes[0].item())
         R = eng.R[0, :N, :N].cpu().numpy()
-        assert np.array_equal(R, R.T, equal_nan=True) and np.isnan(np.diag(R)).all()
+        up = R[np.triu_indices(N, 1)]                                       # only the upper triangle is stored
+        assert np.isnan(np.diag(R)).all() and np.isfinite(up).all() and np.abs(up).max() <= 1.0
         # node series of job 0, area 0: sequential row-major sum of dt * scale over the member cells (ComplexNetworks.py:303-306)
         T0 = int(eng.job_T[0].item())
         mem = np.sort(cells[0, starts[0, 0]:starts[0, 1]])
