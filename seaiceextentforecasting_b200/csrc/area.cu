@@ -35,6 +35,14 @@
 #include <type_traits>
 #include "common.cuh"
 
+// Gathers from R are single-use: with two CTAs per SM only ~10 KB of L1 is left, so by default they are cached in L2
+// only (ld.global.cg) and L1 keeps the dense step-2 scratch.  -DSIE_AREA_LDG restores read-only-path loads (A/B timing).
+#ifdef SIE_AREA_LDG
+#define SIE_RLOAD(p) __ldg(p)
+#else
+#define SIE_RLOAD(p) __ldcg(p)
+#endif
+
 namespace {
 
 constexpr int LEAF = 128;          // numpy's pairwise block size
@@ -311,7 +319,7 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
   auto rrow = [&](int a) -> RowH { RowH h; h.n = a; h.p = R + (size_t)a * (ZR ? Tp : ldn); return h; };
   auto rat = [&](const RowH& h, int c) -> double {
     if constexpr (ZR) return sie_zcorr(h.p, R + (size_t)c * Tp, kT, h.n == c);
-    else return (c >= h.n) ? __ldg(h.p + c) : __ldg(R + (size_t)c * ldn + h.n);   // upper triangle stored: R[min][max]
+    else return (c >= h.n) ? SIE_RLOAD(h.p + c) : SIE_RLOAD(R + (size_t)c * ldn + h.n);   // upper triangle stored: R[min][max]
   };
   const double* sten = stencil_all + (size_t)b * ldn * 4;
   const int32_t* cnode_g = cell_node_all + (size_t)b * C;
@@ -1010,9 +1018,13 @@ AreaPlan plan_area(const SieDevice* dev, int B, int C, int ldn, int max_areas, b
     const size_t i16 = 7 * align_up(sizeof(int16_t) * (size_t)C, 16) + area_tab_bytes(max_areas, sizeof(int16_t)) + 64;
     const size_t s256 = align_up(slot_bytes(AreaCfg<256, int16_t>::FCAP), 16) + i16;
     const size_t s512 = align_up(slot_bytes(AreaCfg<512, int16_t>::FCAP), 16) + i16;
-    // two 256-thread CTAs per SM give ~1.2x the throughput of one 512-thread CTA (a job alone takes 1.3x longer, paired
-    // 1.6x: tools/prof_area.py) -- but only when there are enough jobs to pair them on every SM
-    if (B > 2 * dev->sm_count && 2 * (s256 + 4096 + 1024) <= (size_t)dev->smem_per_sm) {
+    // two 256-thread CTAs per SM against one 512-thread CTA: a job takes 1.3x longer with half the threads and 1.64x
+    // when it shares its SM (tools/prof_area.py), so the pair wins whenever it saves a wave of the persistent grid:
+    // waves x job time, in units of the 512-thread job
+    const int sms = dev->sm_count;
+    const double t512 = (double)((B + sms - 1) / sms);
+    const double t256 = (double)((B + 2 * sms - 1) / (2 * sms)) * (B > sms ? 1.64 : 1.3);
+    if (t256 < t512 && 2 * (s256 + 4096 + 1024) <= (size_t)dev->smem_per_sm) {
       pl.variant = 0; pl.ctas_per_sm = 2; pl.smem = s256; return pl;
     }
     if (s512 <= budget) { pl.variant = 1; pl.smem = s512; return pl; }
