@@ -82,13 +82,14 @@ int sie_detrend_zscore(const double* fields, const int32_t* job_field, const int
  * tau      [B]; tau_sum [B]; tau_cnt [B] (int64)   -- sums are over BOTH triangles like the reference
  * shard_rank/shard_count: tile-row bi is computed by the rank with bi % shard_count == shard_rank
  *     (multi-GPU row-block split; tau is then finished by the caller after an all-reduce of sum/cnt).
- * kernel   SIE_CORR_AUTO: the 128x64 tile kernel when R is stored, the row-resident warp-specialised kernel for the
- *          tau-only pass (R == NULL); SIE_CORR_TILES / SIE_CORR_ROWS force one (both serve both modes and agree
- *          bit for bit).  There is no environment variable or other hidden state behind the choice.
+ * kernel   SIE_CORR_AUTO = SIE_CORR_ROWS: the row-resident warp-specialised kernel (store warps drain the staged tile
+ *          while the consumer warps are in the next tile's MMAs); SIE_CORR_TILES forces the 128x64 tile kernel (both
+ *          serve both modes and agree bit for bit).  There is no environment variable or other hidden state.
  */
 #define SIE_CORR_AUTO 0
 #define SIE_CORR_TILES 1
 #define SIE_CORR_ROWS 2
+#define SIE_CORR_ROWS_MIRROR 3   /* rows kernel that also writes the lower triangle (debug / A-B only) */
 int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32_t* job_T, const double* r_crit,
                  int B, int ldn, int Tp, double* R,
                  double* tile_part, size_t tile_part_bytes,

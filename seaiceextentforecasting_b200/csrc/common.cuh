@@ -10,7 +10,7 @@ void sie_set_error(const char* fmt, ...);
 // Cached facts of one device + the dynamic-shared-memory limit each kernel was last given there (abi.cu).
 #define SIE_MAX_DEVICES 64
 #define SIE_ATTR_SLOTS 16
-enum SieAttrSlot { SIE_K_DETREND = 0, SIE_K_CORR_TILES, SIE_K_CORR_ROWS_ST, SIE_K_CORR_ROWS_TAU, SIE_K_AREA_ON32,
+enum SieAttrSlot { SIE_K_DETREND = 0, SIE_K_CORR_TILES, SIE_K_CORR_ROWS_ST, SIE_K_CORR_ROWS_MIR, SIE_K_CORR_ROWS_TAU, SIE_K_AREA_ON32,
                    SIE_K_AREA_OFF32, SIE_K_AREA_ON16, SIE_K_AREA_ON16_2, SIE_K_AREA_ON32_Z, SIE_K_AREA_OFF32_Z, SIE_K_GP,
                    SIE_K_LINKS };
 struct SieDevice {

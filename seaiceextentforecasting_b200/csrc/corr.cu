@@ -347,7 +347,7 @@ __device__ __forceinline__ double clip_unit(double v) {
   return v;
 }
 
-template <bool STORE>
+template <bool STORE, bool MIRROR>
 __global__ void __launch_bounds__(rw_threads<STORE>(), 1)
 k_corr_rows(const double* __restrict__ z, const long long* __restrict__ prefix, const int4* __restrict__ table,
             int B, int ldn, int Tp, int S, double* __restrict__ R, double* __restrict__ parts) {
@@ -355,7 +355,7 @@ k_corr_rows(const double* __restrict__ z, const long long* __restrict__ prefix, 
   double* sA = reinterpret_cast<double*>(smem_raw);               // [128][Tp]
   double* sB = sA + (size_t)TILE * Tp;                            // [S][64][Tp]
   double* sD = sB + (size_t)S * TILE_N * Tp;                      // [128][RW_D_LD]   (STORE)
-  double* sT = sD + (size_t)TILE * RW_D_LD;                       // [64][RW_T_LD]    (STORE)
+  double* sT = sD + (size_t)TILE * RW_D_LD;                       // [64][RW_T_LD]    (STORE && MIRROR)
   __shared__ uint64_t full_bar[RW_MAXS], empty_bar[RW_MAXS];
   __shared__ uint64_t d_full, d_free, t_full, t_free;             // staging handshakes consumers <-> store warps
 
@@ -429,6 +429,7 @@ k_corr_rows(const double* __restrict__ z, const long long* __restrict__ prefix, 
       __syncwarp();
       if (lane == 0) mbar_arrive(&d_free);
       // its mirror: staged transposed row c -> 1 KB (512 B for the second diagonal tile) of R row col0+c
+      if (!MIRROR) { e = en; continue; }              // upper triangle only: readers address R[min][max]
       mbar_wait(&t_full, k & 1);
       if (dk != 0) {
         const int nh = dk == 1 ? 1 : 2;
@@ -564,6 +565,8 @@ k_corr_rows(const double* __restrict__ z, const long long* __restrict__ prefix, 
     if (STORE) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&d_full);
+    }
+    if (STORE && MIRROR) {
       // ---- pass 2: the transposed tile (nothing for the first diagonal tile and for the diagonal square)
       if (k > 0) mbar_wait(&t_free, (k - 1) & 1);                  // tile k-1 has left sT
       if (dk != 0) {
@@ -717,7 +720,8 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
                             const double* r_crit, int B, int ldn, int Tp, double* R, double* tile_part,
                             size_t tile_part_bytes, double* tau_sum, int64_t* tau_cnt, double* tau,
                             int shard_rank, int shard_count, int kernel, void* stream) {
-  SIE_CHECK_ARG(kernel == SIE_CORR_AUTO || kernel == SIE_CORR_TILES || kernel == SIE_CORR_ROWS, "unknown kernel choice");
+  SIE_CHECK_ARG(kernel == SIE_CORR_AUTO || kernel == SIE_CORR_TILES || kernel == SIE_CORR_ROWS ||
+                    kernel == SIE_CORR_ROWS_MIRROR, "unknown kernel choice");
   SIE_CHECK_ARG(z && n_nodes && job_T && r_crit && tile_part && tau_sum && tau_cnt && tau, "null pointer");
   SIE_CHECK_ARG(B > 0 && ldn > 0 && (ldn % TILE) == 0, "ldn must be a positive multiple of 128");
   SIE_CHECK_ARG(Tp >= 4 && (Tp % 4) == 0, "Tp must be a multiple of 4");
@@ -748,25 +752,29 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
                                                               table);
   SIE_CHECK_LAUNCH();
   // row-resident kernel when its shared memory fits (always for the 1979-2020 windows, Tp <= 44), else the tile kernel
+  const bool mirror = (kernel == SIE_CORR_ROWS_MIRROR);           // also write R[j][i] (readers never need it)
   const size_t rw_fixed = (size_t)TILE * Tp * sizeof(double) +
-                          (R ? ((size_t)TILE * RW_D_LD + (size_t)TILE_N * RW_T_LD) * sizeof(double) : 0);
+                          (R ? ((size_t)TILE * RW_D_LD + (mirror ? (size_t)TILE_N * RW_T_LD : 0)) * sizeof(double) : 0);
   const size_t rw_stage = (size_t)TILE_N * Tp * sizeof(double);
   int S = (size_t)max_optin < rw_fixed + 256 ? 0 : (int)(((size_t)max_optin - 256 - rw_fixed) / rw_stage);
   if (S > RW_MAXS) S = RW_MAXS;
   // default: rows kernel for the tau-only pass (25.2 vs 22.6 TFLOP/s at 25 km), tile kernel when R is stored (2.14 vs
   // 2.29 ms on the 144-network sweep: the staged tile's extra trip through the LSU pipe costs what the resident A
   // panel saves).  `kernel` = SIE_CORR_TILES / SIE_CORR_ROWS overrides (A/B timing, parity tests of both paths).
-  const bool want_rows = kernel == SIE_CORR_AUTO ? (R == nullptr) : (kernel == SIE_CORR_ROWS);
+  const bool want_rows = kernel == SIE_CORR_AUTO ? true : (kernel != SIE_CORR_TILES);
   const bool use_rows = S >= 2 && want_rows;
   if (use_rows) {
     const size_t rsmem = rw_fixed + (size_t)S * rw_stage;
     const int grid = (int)(max_items < sms ? max_items : sms);
-    if (R) {
-      if (int rc = sie_ensure_smem(dev, SIE_K_CORR_ROWS_ST, (const void*)k_corr_rows<true>, rsmem)) return rc;
-      k_corr_rows<true><<<grid, rw_threads<true>(), rsmem, st>>>(z, prefix, table, B, ldn, Tp, S, R, parts);
+    if (R && mirror) {
+      if (int rc = sie_ensure_smem(dev, SIE_K_CORR_ROWS_MIR, (const void*)k_corr_rows<true, true>, rsmem)) return rc;
+      k_corr_rows<true, true><<<grid, rw_threads<true>(), rsmem, st>>>(z, prefix, table, B, ldn, Tp, S, R, parts);
+    } else if (R) {
+      if (int rc = sie_ensure_smem(dev, SIE_K_CORR_ROWS_ST, (const void*)k_corr_rows<true, false>, rsmem)) return rc;
+      k_corr_rows<true, false><<<grid, rw_threads<true>(), rsmem, st>>>(z, prefix, table, B, ldn, Tp, S, R, parts);
     } else {
-      if (int rc = sie_ensure_smem(dev, SIE_K_CORR_ROWS_TAU, (const void*)k_corr_rows<false>, rsmem)) return rc;
-      k_corr_rows<false><<<grid, rw_threads<false>(), rsmem, st>>>(z, prefix, table, B, ldn, Tp, S, R, parts);
+      if (int rc = sie_ensure_smem(dev, SIE_K_CORR_ROWS_TAU, (const void*)k_corr_rows<false, false>, rsmem)) return rc;
+      k_corr_rows<false, false><<<grid, rw_threads<false>(), rsmem, st>>>(z, prefix, table, B, ldn, Tp, S, R, parts);
     }
     SIE_CHECK_LAUNCH();
     k_tau_tiles<<<(unsigned)((max_items + 255) / 256), 256, 0, st>>>(parts, prefix, B, tile_pair);

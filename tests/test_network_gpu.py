@@ -208,7 +208,7 @@ def test_both_correlation_kernels_agree(lib_built, X, Y, Ts, latlon):
     """`sie_corr_tau` has two kernels (csrc/corr.cu): the tile kernel (default when R is stored) and the row-resident,
     warp-specialised one (default for the tau-only pass).  Either can serve either mode (the `kernel` argument): the stored
     upper triangle of R (what every reader addresses, R[min][max]) must be bitwise identical with a NaN diagonal and no
-    element left unwritten, the count identical and tau within 1e-12; the rows kernel also writes the mirror image, which
+    element left unwritten, the count identical and tau within 1e-12; SIE_CORR_ROWS_MIRROR also writes the mirror image, which
     must equal it bitwise; R matches numpy's corrcoef of the detrended nodes to 1e-9 (ComplexNetworks.py:34-35)."""
     import torch
     from seaiceextentforecasting_b200.engine import NetworkBatch, h2d, r_crit_ttest
@@ -225,7 +225,7 @@ def test_both_correlation_kernels_agree(lib_built, X, Y, Ts, latlon):
     N = eng.n_nodes.cpu().numpy()
     out = {}
     from seaiceextentforecasting_b200 import _lib
-    for kern, kid in (("tiles", _lib.SIE_CORR_TILES), ("rows", _lib.SIE_CORR_ROWS)):
+    for kern, kid in (("tiles", _lib.SIE_CORR_TILES), ("rows", _lib.SIE_CORR_ROWS), ("mirror", _lib.SIE_CORR_ROWS_MIRROR)):
         eng.R.fill_(-7.0)
         eng.corr_tau(rc, store_R=True, kernel=kid)
         torch.cuda.synchronize()
@@ -235,11 +235,12 @@ def test_both_correlation_kernels_agree(lib_built, X, Y, Ts, latlon):
         torch.cuda.synchronize()
         out[kern] = (Rs, stored, (eng.tau.cpu().numpy().copy(), eng.tau_cnt.cpu().numpy().copy()))
     for b in range(B):
-        a, c = out["tiles"][0][b], out["rows"][0][b]
+        a, c, f = out["tiles"][0][b], out["rows"][0][b], out["mirror"][0][b]
         iu = np.triu_indices(a.shape[0], 1)
-        assert np.array_equal(a[iu], c[iu]) and not (a[iu] == -7.0).any() and np.isfinite(a[iu]).all()
-        assert np.isnan(np.diag(a)).all() and np.isnan(np.diag(c)).all()
-        assert np.array_equal(c, c.T, equal_nan=True) and not (c == -7.0).any()
+        assert np.array_equal(a[iu], c[iu]) and np.array_equal(a[iu], f[iu])
+        assert not (a[iu] == -7.0).any() and np.isfinite(a[iu]).all()
+        assert np.isnan(np.diag(a)).all() and np.isnan(np.diag(c)).all() and np.isnan(np.diag(f)).all()
+        assert np.array_equal(f, f.T, equal_nan=True) and not (f == -7.0).any()       # the mirror-writing variant
     dtb = eng.dt[0, :, :Ts[0]].cpu().numpy()
     nodes = eng.node_cell[0, :N[0]].cpu().numpy()
     ref = np.corrcoef(dtb[nodes])

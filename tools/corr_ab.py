@@ -6,6 +6,7 @@ from seaiceextentforecasting_b200 import _lib
 from seaiceextentforecasting_b200.engine import NetworkBatch, h2d, r_crit_ttest
 
 KERNELS = (("tiles", _lib.SIE_CORR_TILES), ("rows", _lib.SIE_CORR_ROWS))
+STORED = KERNELS + (("mirror", _lib.SIE_CORR_ROWS_MIRROR),)
 
 
 def timed(fn, reps=5):
@@ -29,15 +30,16 @@ def stored(X, Y, Ts, latlon=False):
     rc = h2d(np.array([r_crit_ttest(t, 0.01) for t in Ts]))
     eng.detrend_zscore(fields, jf, jT, True); torch.cuda.synchronize()
     out = {}
-    for kern, kid in KERNELS:
+    for kern, kid in STORED:
         eng.R.fill_(-7.0)
         eng.corr_tau(rc, store_R=True, kernel=kid); torch.cuda.synchronize()
         N = eng.n_nodes.cpu().numpy()
         out[kern] = ([eng.R[b, :N[b], :N[b]].cpu().numpy().copy() for b in range(min(B, 6))], eng.tau.cpu().numpy().copy(),
                      eng.tau_cnt.cpu().numpy().copy())
         ms = timed(lambda: eng.corr_tau(rc, store_R=True, kernel=kid))
-        byts = float(((4.0 if kern == "tiles" else 8.0) * N.astype(np.float64) ** 2).sum())
-        print(f"{X}x{Y} B={B} {kern}: {ms:.3f} ms  {byts/ms/1e6:.0f} GB/s stored (4N^2 tiles / 8N^2 rows)  N={N[0]} ldn={eng.ldn}")
+        byts = float(((8.0 if kern == "mirror" else 4.0) * N.astype(np.float64) ** 2).sum())
+        flop = float((N.astype(np.float64) * (N + 1.0) * np.asarray(Ts, dtype=np.float64)).sum())
+        print(f"{X}x{Y} B={B} {kern}: {ms:.3f} ms  {byts/ms/1e6:.0f} GB/s stored (4N^2; mirror 8N^2), {flop/ms/1e9:.1f} TFLOP/s  N={N[0]} ldn={eng.ldn}")
     for b, (a, c) in enumerate(zip(out["tiles"][0], out["rows"][0])):
         iu = np.triu_indices(a.shape[0], 1)
         same = np.array_equal(a[iu], c[iu])            # the tile kernel stores the upper triangle only
