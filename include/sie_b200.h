@@ -82,9 +82,9 @@ int sie_detrend_zscore(const double* fields, const int32_t* job_field, const int
  * tau      [B]; tau_sum [B]; tau_cnt [B] (int64)   -- sums are over BOTH triangles like the reference
  * shard_rank/shard_count: tile-row bi is computed by the rank with bi % shard_count == shard_rank
  *     (multi-GPU row-block split; tau is then finished by the caller after an all-reduce of sum/cnt).
- * kernel   SIE_CORR_AUTO = SIE_CORR_ROWS: the row-resident warp-specialised kernel (store warps drain the staged tile
- *          while the consumer warps are in the next tile's MMAs); SIE_CORR_TILES forces the 128x64 tile kernel (both
- *          serve both modes and agree bit for bit).  There is no environment variable or other hidden state.
+ * kernel   SIE_CORR_AUTO: the 128x64 tile kernel when R is stored, the row-resident warp-specialised kernel for the
+ *          tau-only pass (R == NULL); SIE_CORR_TILES / SIE_CORR_ROWS force one (both serve both modes and give the
+ *          same upper triangle bit for bit).  There is no environment variable or other hidden state.
  */
 #define SIE_CORR_AUTO 0
 #define SIE_CORR_TILES 1

@@ -309,6 +309,9 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
   const int b = sh_job;
   if (b >= B) break;
   unsigned long long wk = 0;   // correlations consumed (algorithmic gathers)
+#ifdef SIE_AREA_PHASE_TIMERS
+  unsigned long long rbucket[6] = {0, 0, 0, 0, 0, 0};
+#endif
   unsigned long long bph[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // bookkeeping-warp phase cycles (its lane 0), work[16..23]
   const int N = min(n_nodes[b], ldn);
   const double tau = tau_all[b];
@@ -653,6 +656,10 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
     if (bw.ord <= 1ull) break;   // no areas at all (:212) or all finalised
     const int best = (int)bw.a;
     ++n_rounds;
+#ifdef SIE_AREA_PHASE_TIMERS
+    const long long round_t0 = clock64();
+    const int round_nb0 = S.size[best];
+#endif
     if (best != cur_best) {                    // materialise V[best] in list order
       int off = 0;
       for (int s = best; s >= 0; s = S.seg_next[s]) {
@@ -943,6 +950,12 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
     }
     __syncthreads();
     TICK(12);                             // winner, merge / finalise, dense block extension
+#ifdef SIE_AREA_PHASE_TIMERS
+    if (tid == 0) {    // rounds bucketed by the size of the best area: (count << 44) | cycles, work[26..31]
+      const int bk = round_nb0 <= 4 ? 0 : round_nb0 <= 8 ? 1 : round_nb0 <= 16 ? 2 : round_nb0 <= 32 ? 3 : round_nb0 <= 64 ? 4 : 5;
+      rbucket[bk] += (1ull << 44) + (unsigned long long)(clock64() - round_t0);
+    }
+#endif
   }
 
   // =============================================================== output in dict order (ascending key)
@@ -957,6 +970,9 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
     for (int i = 0; i < 11; ++i) work_all[SIE_AREA_WORK * b + 4 + i] = ph[i];
     work_all[SIE_AREA_WORK * b + 24] = ph[11];
     work_all[SIE_AREA_WORK * b + 25] = ph[12];
+#ifdef SIE_AREA_PHASE_TIMERS
+    for (int i = 0; i < 6; ++i) work_all[SIE_AREA_WORK * b + 26 + i] = rbucket[i];
+#endif
     work_all[SIE_AREA_WORK * b + 15] = n_slow;
   }
   if (tid == BKW * 32 && work_all)

@@ -761,7 +761,10 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
   // default: rows kernel for the tau-only pass (25.2 vs 22.6 TFLOP/s at 25 km), tile kernel when R is stored (2.14 vs
   // 2.29 ms on the 144-network sweep: the staged tile's extra trip through the LSU pipe costs what the resident A
   // panel saves).  `kernel` = SIE_CORR_TILES / SIE_CORR_ROWS overrides (A/B timing, parity tests of both paths).
-  const bool want_rows = kernel == SIE_CORR_AUTO ? true : (kernel != SIE_CORR_TILES);
+  // default: rows kernel for the tau-only pass (25.2 vs 22.6 TFLOP/s at 25 km), tile kernel when R is stored (0.277 vs
+  // 0.325 ms on 24 57x57 networks, tools/corr_ab.py: the rows kernel's staging trip through shared memory costs more
+  // than its resident A panel and its store warps save)
+  const bool want_rows = kernel == SIE_CORR_AUTO ? (R == nullptr) : (kernel != SIE_CORR_TILES);
   const bool use_rows = S >= 2 && want_rows;
   if (use_rows) {
     const size_t rsmem = rw_fixed + (size_t)S * rw_stage;

@@ -246,7 +246,7 @@ def test_both_correlation_kernels_agree(lib_built, X, Y, Ts, latlon):
     ref = np.corrcoef(dtb[nodes])
     np.fill_diagonal(ref, np.nan)
     m = ~np.isnan(ref)
-    assert np.max(np.abs(out["rows"][0][0][m] - ref[m])) <= 1e-9
+    assert np.max(np.abs(out["mirror"][0][0][m] - ref[m])) <= 1e-9
     for mode in (1, 2):
         assert np.array_equal(out["tiles"][mode][1], out["rows"][mode][1])
         np.testing.assert_allclose(out["tiles"][mode][0], out["rows"][mode][0], rtol=1e-12)

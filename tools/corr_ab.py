@@ -43,7 +43,8 @@ def stored(X, Y, Ts, latlon=False):
     for b, (a, c) in enumerate(zip(out["tiles"][0], out["rows"][0])):
         iu = np.triu_indices(a.shape[0], 1)
         same = np.array_equal(a[iu], c[iu])            # the tile kernel stores the upper triangle only
-        sym = np.array_equal(c, c.T, equal_nan=True)
+        f = out["mirror"][0][b]
+        sym = np.array_equal(f, f.T, equal_nan=True) and np.array_equal(f[iu], a[iu])     # the mirror-writing variant
         print(f"  job {b}: R bitwise equal {same}, symmetric {sym}, diag NaN {np.isnan(np.diag(c)).all()}, untouched {(c == -7.0).sum()}")
         assert same and sym
     print("  tau rel diff", np.abs(out["tiles"][1] - out["rows"][1]).max() / np.abs(out["tiles"][1]).max(), "cnt equal", np.array_equal(out["tiles"][2], out["rows"][2]))

@@ -17,7 +17,7 @@ M = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 ws = [bench.make_workload(m) for m in range(M)]
 names = ['seed', 'argmax', 'create', 'update+gather', 's2.select', 's2.discover', 's2.lists', 's2.rowmeans', 's2.stat',
          's2.fill', 'eval']
-for MA in (768, 1024):
+for MA in (768,) if len(sys.argv) > 2 else (768, 1024):
     sw = RetrospectiveSweep(NORTH_INITS, [w["sic"] for w in ws], ws[0]["sie"], bench.FMIN, bench.FMAX, ws[0]["psar"],
                             [w["sst"] for w in ws], ws[0]["lat"], max_areas=MA)
     sw.upload()
@@ -43,5 +43,9 @@ for MA in (768, 1024):
                   "merge", round(float(wk[:, 25].sum()) / 1e6, 1), "owner-wait", round(float(wk[:, 24].sum()) / 1e6, 1))
             print("   BK warp Mcyc outside/detect/assign/init/tail:",
                   [round(float(wk[:, 16 + i].sum()) / 1e6, 1) for i in range(5)])
+            rb = wk[:, 26:32].astype(np.uint64)
+            cnt, cyc = (rb >> np.uint64(44)).sum(axis=0), (rb & np.uint64((1 << 44) - 1)).sum(axis=0)
+            print("   merge rounds by best-area size (<=4, <=8, <=16, <=32, <=64, >64): count", cnt.tolist(),
+                  "Mcyc", [round(float(c) / 1e6, 1) for c in cyc], "kcyc/round", [round(float(c) / max(1, int(n)) / 1e3, 1) for c, n in zip(cyc, cnt)])
     del sw
     torch.cuda.empty_cache()
