@@ -498,6 +498,143 @@ __device__ void cta_chol_solve(const double* L, int n, const double* b, double* 
   __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-local fit for the hyper-parameter grid: one warp owns one (problem, l, sigma) evaluation -- its own n x n
+// kernel matrix in shared memory (row stride ldw = n | 1), right-looking Cholesky with a row per lane, triangular
+// solves with lane-split dot products -- so the 8 warps of a CTA factor 8 different sigma at once instead of taking
+// turns at CTA-wide barriers.  Every element receives the same sequence of fma updates as in cta_cholesky (k = 0, 1,
+// ... in order), so the factor is bit-identical to the CTA-wide path.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_cholesky(double* K, int n, int ldw, int lane) {
+  for (int k = 0; k < n; ++k) {
+    const double d = K[k * ldw + k];
+    if (!(d > 0.0)) return k + 1;          // uniform across the warp
+    const double r = sqrt(d);
+    __syncwarp();
+    if (lane == 0) K[k * ldw + k] = r;
+    for (int i = k + 1 + lane; i < n; i += 32) K[i * ldw + k] /= r;
+    __syncwarp();
+    for (int i = k + 1 + lane; i < n; i += 32) {
+      const double aik = K[i * ldw + k];
+      for (int jj = k + 1; jj <= i; ++jj) K[i * ldw + jj] = fma(-aik, K[jj * ldw + k], K[i * ldw + jj]);
+    }
+    __syncwarp();
+  }
+  return 0;
+}
+__device__ __forceinline__ void warp_fwd_solve_ld(const double* L, int n, int ldw, const double* b, double* tmp, int lane) {
+  for (int i = 0; i < n; ++i) {
+    double s = 0.0;
+    for (int c = lane; c < i; c += 32) s = fma(L[i * ldw + c], tmp[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) tmp[i] = (b[i] - s) / L[i * ldw + i];
+    __syncwarp();
+  }
+}
+__device__ __forceinline__ void warp_bwd_solve_ld(const double* L, int n, int ldw, const double* tmp, double* x, int lane) {
+  for (int i = n - 1; i >= 0; --i) {
+    double s = 0.0;
+    for (int c = i + 1 + lane; c < n; c += 32) s = fma(L[c * ldw + i], x[c], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) x[i] = (tmp[i] - s) / L[i * ldw + i];
+    __syncwarp();
+  }
+}
+
+// One (sigma) evaluation by one warp.  W: n x n (stride LDS, shared, read-only); y, kxs_raw: shared, read-only;
+// Kw / vec: this warp's workspace (n x ldw and 4 x MAXN doubles); G1raw: X (M Sigma~) X^T (stride LDS, global) or null.
+__device__ void warp_sigma_fit(const double* __restrict__ W, const double* __restrict__ y, const double* __restrict__ kxs_raw,
+                               double kss_raw, const double* __restrict__ G1raw, int n, double sig, double* Kw, double* vec,
+                               SieGpResult& res, long long clk_start, SieGpResult* outp) {
+  const int lane = threadIdx.x & 31;
+  const int ldw = n | 1;
+  double* ya = vec; double* alpha = vec + MAXN; double* kxs = vec + 2 * MAXN; double* v = vec + 3 * MAXN;
+  res.fmean = res.fvar = res.sigma_f = res.nlml = res.g_ell = res.g_sig = sie_nan();
+  res.info = 0;
+  for (int idx = lane; idx < n * n; idx += 32) {
+    const int i = idx / n, jj = idx - i * n;
+    Kw[i * ldw + jj] = W[i * LDS + jj] + ((i == jj) ? sig : 0.0);
+  }
+  __syncwarp();
+  int info = warp_cholesky(Kw, n, ldw, lane);
+  if (info) { if (lane == 0) { res.info = info; res.cycles_total = clock64() - clk_start; *outp = res; } return; }
+  warp_fwd_solve_ld(Kw, n, ldw, y, v, lane);
+  warp_bwd_solve_ld(Kw, n, ldw, v, ya, lane);
+  double sf = 0.0;
+  for (int t = 0; t < n; ++t) sf = fma(y[t], ya[t], sf);
+  sf /= (double)n;
+  const double sn = sf * sig;
+  res.sigma_f = sf;
+  __syncwarp();
+  for (int idx = lane; idx < n * n; idx += 32) {
+    const int i = idx / n, jj = idx - i * n;
+    Kw[i * ldw + jj] = sf * W[i * LDS + jj] + ((i == jj) ? sn : 0.0);
+  }
+  __syncwarp();
+  info = warp_cholesky(Kw, n, ldw, lane);
+  if (info) { if (lane == 0) { res.info = info; res.cycles_total = clock64() - clk_start; *outp = res; } return; }
+  warp_fwd_solve_ld(Kw, n, ldw, y, v, lane);
+  warp_bwd_solve_ld(Kw, n, ldw, v, alpha, lane);
+  for (int i = lane; i < n; i += 32) kxs[i] = sf * kxs_raw[i];
+  __syncwarp();
+  const double kss = sf * kss_raw + sn;
+  warp_fwd_solve_ld(Kw, n, ldw, kxs, v, lane);
+  double vv = 0.0, fm = 0.0, yal = 0.0, ld_sum = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    vv = fma(v[i], v[i], vv);
+    fm = fma(kxs[i], alpha[i], fm);
+    yal = fma(y[i], alpha[i], yal);
+    ld_sum += log(Kw[i * ldw + i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vv += __shfl_xor_sync(0xffffffffu, vv, o);
+    fm += __shfl_xor_sync(0xffffffffu, fm, o);
+    yal += __shfl_xor_sync(0xffffffffu, yal, o);
+    ld_sum += __shfl_xor_sync(0xffffffffu, ld_sum, o);
+  }
+  res.fmean = fm; res.fvar = kss - vv;
+  res.nlml = yal / 2 + ld_sum + n * log(2 * 3.141592653589793238462643383279502884) / 2;
+  if (G1raw) {
+    // MLII gradient as written (:248-252): dK/dl = sf G1raw + sn I, dK/dsigma = sf W + sf I
+    for (int which = 0; which < 2; ++which) {
+      auto dK = [&](int i, int jj) -> double {
+        return which == 0 ? sf * G1raw[i * LDS + jj] + ((i == jj) ? sn : 0.0) : sf * W[i * LDS + jj] + ((i == jj) ? sf : 0.0);
+      };
+      double quad = 0.0;
+      for (int idx = lane; idx < n * n; idx += 32) {
+        const int i = idx / n, jj = idx - i * n;
+        quad = fma(alpha[i] * dK(i, jj), alpha[jj], quad);
+      }
+      double tr = 0.0;
+      for (int jj = lane; jj < n; jj += 32) {          // column jj of K^-1 dK, down to its diagonal entry
+        double col[MAXN];
+        for (int i = 0; i < n; ++i) {
+          double sacc = dK(i, jj);
+          for (int c = 0; c < i; ++c) sacc = fma(-Kw[i * ldw + c], col[c], sacc);
+          col[i] = sacc / Kw[i * ldw + i];
+        }
+        for (int i = n - 1; i >= jj; --i) {
+          double sacc = col[i];
+          for (int c = i + 1; c < n; ++c) sacc = fma(-Kw[c * ldw + i], col[c], sacc);
+          col[i] = sacc / Kw[i * ldw + i];
+        }
+        tr += col[jj];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        quad += __shfl_xor_sync(0xffffffffu, quad, o);
+        tr += __shfl_xor_sync(0xffffffffu, tr, o);
+      }
+      const double gval = tr / 2 - quad / 2;
+      if (which == 0) res.g_ell = gval; else res.g_sig = gval;
+    }
+  }
+  if (lane == 0) { res.cycles_total = clock64() - clk_start; *outp = res; }
+}
+
 __global__ void __launch_bounds__(GT, 2)
 k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __restrict__ y_all,
               const double* __restrict__ anom_sic, const int32_t* __restrict__ n_areas_sic, int ma_sic, int ts_sic,
@@ -670,6 +807,44 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
     if (pr.want_grad) {        // sigma-independent part of the MLII gradient: X (M Sigma~) (:248)
       cta_gemm(buf[5], ld, M, ld, E, ld, np_, np_, np_, sm);
       cta_gemm(XM, ld, Xg, ld, buf[5], ld, n, np_, np_, sm);
+    }
+    if (sig_grid) {
+      // ---- hyper-parameter grid: the sigma-independent pieces once, then one warp per sigma
+      for (int i = tid; i < n; i += GT) {                      // KXXs / sf = X Sigma~ Xs^T
+        double sacc = 0.0;
+        for (int c = 0; c < np_; ++c) sacc = fma(XE[(size_t)i * ld + c], Xg[(size_t)n * ld + c], sacc);
+        sm.kxs[i] = sacc;
+      }
+      double kss_part = 0.0;                                   // (KXsXs - sn) / sf = Xs Sigma~ Xs^T
+      for (int c = tid; c < np_; c += GT) {
+        double row = 0.0;
+        for (int d = 0; d < np_; ++d) row = fma(Xg[(size_t)n * ld + d], E[(size_t)d * ld + c], row);
+        kss_part = fma(row, Xg[(size_t)n * ld + c], kss_part);
+      }
+      const double kss_raw = block_sum(kss_part, sm);
+      if (pr.want_grad) {                                      // X (M Sigma~) X^T, sigma-independent
+        for (int idx = tid; idx < n * n; idx += GT) {
+          const int i = idx / n, jj = idx - i * n;
+          double sacc = 0.0;
+          for (int c = 0; c < np_; ++c) sacc = fma(XM[(size_t)i * ld + c], Xg[(size_t)jj * ld + c], sacc);
+          Gg[i * LDS + jj] = sacc;
+        }
+      }
+      __syncthreads();
+      // per-warp workspaces over the GEMM staging buffers and the (unused here) CTA-wide K: As | Bs | u.gp.K
+      double* wsp = &sm.As[0][0];
+      const size_t avail = (size_t)(&sm.u.gp.W[0] - wsp);
+      const size_t per_warp = (size_t)n * (n | 1) + 4 * MAXN;
+      int nwu = (int)(avail / per_warp);
+      if (nwu > GT / 32) nwu = GT / 32;
+      const int warp = tid >> 5;
+      if (warp < nwu) {
+        double* Kw = wsp + (size_t)warp * per_warp;
+        for (int ks = warp; ks < ns; ks += nwu)
+          warp_sigma_fit(sm.u.gp.W, sm.y, sm.kxs, kss_raw, pr.want_grad ? Gg : nullptr, n, sig_grid[ks], Kw,
+                         Kw + (size_t)n * (n | 1), res, clk_start, out + (size_t)p * ns + ks);
+      }
+      continue;                                                // next problem (the loop head synchronises the CTA)
     }
     for (int ks = 0; ks < ns; ++ks) {
     const double sig = sig_grid ? sig_grid[ks] : pr.sig;
