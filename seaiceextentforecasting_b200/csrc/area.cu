@@ -866,15 +866,12 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
           int nanc = 0;
           double sum = 0.0;
           if (len > 0) {
-            if (p < nb) {
-              const RowH row = rrow(hn[p]);
-              const int nbb = nb - 1 - p;              // elements of the row inside the best area
-              sum = sie_pw_sum8<MAXD>([&](int i) { const IT* q = (i < nbb) ? hn + (p + 1 + i) : kn + max(i - nbb, 0); return rat(row, *q); }, len, j, gmask, nanc);
-            } else {
-              const RowH row = rrow(kn[p - nb]);
-              const IT* kq = kn + (p - nb) + 1;
-              sum = sie_pw_sum8<MAXD>([&](int i) { return rat(row, kq[i]); }, len, j, gmask, nanc);
-            }
+            // row p of the hypothetical area best ++ k: a best row continues into k's cells, a row of k stays in k
+            const bool in_best = p < nb;
+            const RowH row = rrow(in_best ? hn[p] : kn[p - nb]);
+            const int nbb = in_best ? nb - 1 - p : 0;  // elements of the row inside the best area
+            const IT* kq = in_best ? kn : kn + (p - nb) + 1;
+            sum = sie_pw_sum8<MAXD>([&](int i) { const IT* q = (i < nbb) ? hn + (p + 1 + i) : kq + (i - nbb); return rat(row, *q); }, len, j, gmask, nanc);
             nanc += __shfl_xor_sync(gmask, nanc, 1);
             nanc += __shfl_xor_sync(gmask, nanc, 2);
             nanc += __shfl_xor_sync(gmask, nanc, 4);

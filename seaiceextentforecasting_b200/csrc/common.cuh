@@ -112,9 +112,9 @@ __device__ __forceinline__ void sie_pw_lane8(Get get, int lo, int n, int ngrp, i
 template <typename Get>
 __device__ __forceinline__ void sie_pw_lane8_any(Get get, int lo, int n, int ngrp, int ntail, int j, double& acc,
                                                  double& tv, int& nan_cnt) {
-  if (ngrp <= 1) sie_pw_lane8<1>(get, lo, n, ngrp, ntail, j, acc, tv, nan_cnt);
-  else if (ngrp <= 4) sie_pw_lane8<4>(get, lo, n, ngrp, ntail, j, acc, tv, nan_cnt);
-  else if (ngrp <= 8) sie_pw_lane8<8>(get, lo, n, ngrp, ntail, j, acc, tv, nan_cnt);
+  // two unrolled variants only (<= 32 elements, <= 128): every call site inlines them, and the domain-growth kernel's
+  // instruction footprint matters (two CTAs in different phases share an SM's instruction cache)
+  if (ngrp <= 4) sie_pw_lane8<4>(get, lo, n, ngrp, ntail, j, acc, tv, nan_cnt);
   else sie_pw_lane8<16>(get, lo, n, ngrp, ntail, j, acc, tv, nan_cnt);
 }
 
@@ -168,9 +168,7 @@ __device__ __forceinline__ double sie_pw_leaf8_contig_n(const double* q, int ngr
 }
 __device__ __forceinline__ double sie_pw_leaf8_contig(const double* q, int n, int j, unsigned gmask) {
   const int ngrp = (n < 8) ? 0 : (n >> 3), nt = n - 8 * ngrp;
-  if (ngrp <= 1) return sie_pw_leaf8_contig_n<1>(q, ngrp, nt, j, gmask);
   if (ngrp <= 4) return sie_pw_leaf8_contig_n<4>(q, ngrp, nt, j, gmask);
-  if (ngrp <= 8) return sie_pw_leaf8_contig_n<8>(q, ngrp, nt, j, gmask);
   return sie_pw_leaf8_contig_n<16>(q, ngrp, nt, j, gmask);
 }
 
@@ -181,7 +179,7 @@ __device__ __forceinline__ double sie_pw_leaf8_contig(const double* q, int n, in
 // MAXD = tree depth supported: n <= 128 * 2^MAXD.
 template <int MAXD, typename Leaf>
 __device__ __forceinline__ double sie_pw_tree(Leaf leaf, int n) {
-  if (n <= 128) return leaf(0, n);
+  // (n <= 128 runs the loop once with depth 0: ONE inlined copy of the leaf per call site keeps the code small)
   double val[MAXD];
   unsigned path = 0u;
   int depth = 0, lo = 0, len = n;
