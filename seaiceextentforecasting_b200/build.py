@@ -15,7 +15,9 @@ SOURCES = ["abi.cu", "detrend.cu", "corr.cu", "area.cu", "links.cu", "gp.cu", "i
 # SIE_AREA_TIMERS=1: per-phase clock64 counters of k_area_level (work[4..]); they cost ~6 % of the kernel, so the
 # product build leaves them out (tools/prof_sweep.py and tools/prof_one.py need a build with them)
 NVCC_FLAGS = (["-DSIE_AREA_PHASE_TIMERS"] if os.environ.get("SIE_AREA_TIMERS") else []) + \
-    (["-DSIE_AREA_LDG"] if os.environ.get("SIE_AREA_LDG") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    (["-DSIE_AREA_LDG"] if os.environ.get("SIE_AREA_LDG") else []) + \
+    (["-D" + f for f in os.environ.get("SIE_DEFINES", "").split() if f]) + \
+    (["-DSIE_PW_SMALL_NQ=" + os.environ["SIE_PW_SMALL_NQ"]] if os.environ.get("SIE_PW_SMALL_NQ") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 
 

@@ -72,12 +72,12 @@ struct AreaCfg {
 enum : int { PL_LAB = 1, PL_FKEY = 2, PL_FLIST = 4, PL_HN = 8, PL_HC = 16, PL_CNL = 32, PL_KNL = 64, PL_AREA = 128 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-__host__ __device__ inline size_t rm_cap(int C) { return (size_t)4 * C + 1024; }
+__host__ __device__ inline size_t rm_cap(int C) { return (size_t)4 * C + 1024 + 256; }     // + read-ahead pad
 __host__ __device__ inline int d_cap(int C) { return C < DCAP_MAX ? C : DCAP_MAX; }
 __host__ __device__ inline size_t area_tab_bytes(int MA, size_t isz) {       // 12 integer tables + okey + stat
   return 12 * align_up(isz * (size_t)(MA + 1), 16) + 2 * align_up(sizeof(double) * (size_t)MA, 16);
 }
-__host__ __device__ inline size_t self_cap(int C) { return (size_t)2 * C + 64; }
+__host__ __device__ inline size_t self_cap(int C) { return (size_t)2 * C + 64; }           // allocation adds a read-ahead pad
 __host__ __device__ inline size_t slot_bytes(int fcap) { return sizeof(double) * (18 * (size_t)fcap) + sizeof(int32_t) * 2 * (size_t)fcap; }
 constexpr size_t QUEUE_BYTES = 256;                         // head of the scratch: the job-queue counter
 __host__ __device__ inline size_t scratch_per_cta(int C, int MA) {
@@ -87,7 +87,7 @@ __host__ __device__ inline size_t scratch_per_cta(int C, int MA) {
   s += align_up(sizeof(double) * rm_cap(C), 256);           // rowmean
   s += align_up(sizeof(double) * ((size_t)d_cap(C) * d_cap(C) + 128), 256);   // dmat (+ read-ahead pad)
   s += align_up(area_tab_bytes(MA, sizeof(int32_t)), 256);  // fallback for the per-area tables
-  s += align_up(sizeof(double) * self_cap(C), 256);         // cached self row means of candidate areas
+  s += align_up(sizeof(double) * (self_cap(C) + 256), 256);   // cached self row means of candidate areas (+ read-ahead pad)
   return s;
 }
 
@@ -194,6 +194,62 @@ __device__ __forceinline__ Rec block_arg(const Rec& v, RecSlot* slots, int& par)
   return warp_arg<PW>(t);
 }
 
+// numpy pairwise sum (8-lane group, lane j) of the sequence a[0..na) ++ b[0..n-na) held in (global) memory: leaves that
+// lie inside one run are read with immediate-offset loads, others (and leaves holding a NaN) element by element with
+// NaN screening.  ONE out-of-line copy serves the row means and the statistics of every merge round: the kernel's hot
+// instruction footprint, not its arithmetic, limits two co-resident CTAs (profiles/r02_*).  Reads up to 135 doubles past
+// the end of a run (masked out of the sum): the scratch buffers are padded accordingly.
+#ifdef SIE_AREA_INLINE_RUNS
+#define SIE_RUNS_ATTR __forceinline__
+#else
+#define SIE_RUNS_ATTR __noinline__
+#endif
+#ifdef SIE_AREA_INLINE_GATHER
+#define SIE_GATHER_ATTR __forceinline__
+#else
+#define SIE_GATHER_ATTR __noinline__
+#endif
+template <int MAXD>
+__device__ SIE_RUNS_ATTR double sie_pw_sum_runs(const double* __restrict__ a, int na, const double* __restrict__ b, int n,
+                                               int j, unsigned gmask, int* nan_out) {
+  int nanc = 0;
+  const double sum = sie_pw_tree<MAXD>([&](int lo, int ln) -> double {
+    if (lo + ln <= na || lo >= na) {
+      const double r = sie_pw_leaf8_contig((lo >= na ? b + (lo - na) : a + lo) + j, ln, j, gmask);
+      if (r == r) return r;
+    }
+    return sie_pw_leaf8([&](int i) { return i < na ? a[i] : b[i - na]; }, lo, ln, j, gmask, nanc);
+  }, n);
+  nanc += __shfl_xor_sync(gmask, nanc, 1);
+  nanc += __shfl_xor_sync(gmask, nanc, 2);
+  nanc += __shfl_xor_sync(gmask, nanc, 4);
+  *nan_out = nanc;
+  return sum;
+}
+
+struct RCtx { const double* R; int ldn, Tp, kT; };    // where correlations come from: R (stride ldn) or z rows (stride Tp)
+__device__ double sie_zcorr(const double* __restrict__ za, const double* __restrict__ zc, int kT, bool diag);
+template <bool ZR>
+__device__ __forceinline__ double sie_rat(const RCtx& cx, int a, int c) {
+  if constexpr (ZR) return sie_zcorr(cx.R + (size_t)a * cx.Tp, cx.R + (size_t)c * cx.Tp, cx.kT, a == c);
+  else return (c >= a) ? SIE_RLOAD(cx.R + (size_t)a * cx.ldn + c) : SIE_RLOAD(cx.R + (size_t)c * cx.ldn + a);   // R[min][max]
+}
+// numpy pairwise sum of the correlations of node `rown` with the nodes ia[0..na) ++ ib[0..n-na) (index lists in shared
+// or global memory), NaN entries screened and counted: one out-of-line copy for the re-summing growth steps, the
+// neighbours' own row means and the gather path of the merge rounds.
+template <int MAXD, typename IT, bool ZR>
+__device__ SIE_GATHER_ATTR double sie_pw_sum_gather(RCtx cx, int rown, const IT* ia, int na, const IT* ib, int n, int j,
+                                                 unsigned gmask, int* nan_out) {
+  int nanc = 0;
+  const double sum = sie_pw_sum8<MAXD>([&](int i) { return sie_rat<ZR>(cx, rown, (int)(i < na ? ia[i] : ib[i - na])); },
+                                       n, j, gmask, nanc);
+  nanc += __shfl_xor_sync(gmask, nanc, 1);
+  nanc += __shfl_xor_sync(gmask, nanc, 2);
+  nanc += __shfl_xor_sync(gmask, nanc, 4);
+  *nan_out = nanc;
+  return sum;
+}
+
 // Correlation of nodes a and c recomputed from their unit-norm rows (R not stored: `ZR` instantiations): the same
 // dot product the correlation kernel accumulates (sequential in k), clipped, NaN on the diagonal.
 __device__ __noinline__ double sie_zcorr(const double* __restrict__ za, const double* __restrict__ zc, int kT, bool diag) {
@@ -278,7 +334,7 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
   const int dcap = d_cap(C);
   double* D = (double*)gtake(sizeof(double) * ((size_t)dcap * dcap + 128));
   unsigned char* gtabs = gtake(area_tab_bytes(MA, sizeof(int32_t)));
-  double* selfbuf = (double*)gtake(sizeof(double) * self_cap(C));
+  double* selfbuf = (double*)gtake(sizeof(double) * (self_cap(C) + 256));
   // ---- shared memory: slot state | per-area tables | integer arrays (whatever `place` keeps on chip)
   unsigned char* sp = smem_raw;
   auto stake = [&](size_t bytes) { unsigned char* r = sp; sp += align_up(bytes, 16); return r; };
@@ -318,6 +374,7 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
   // ZR: `Rall` holds the unit-norm rows z [B][ldn][Tp] and every correlation is recomputed from them
   const double* R = ZR ? Rall + (size_t)b * ldn * Tp : Rall + (size_t)b * ldn * ldn;
   const int kT = ZR ? ((job_T[b] + 3) & ~3) : 0;
+  const RCtx rcx = {R, ldn, Tp, kT};
   struct RowH { const double* p; int n; };
   auto rrow = [&](int a) -> RowH { RowH h; h.n = a; h.p = R + (size_t)a * (ZR ? Tp : ldn); return h; };
   auto rat = [&](const RowH& h, int c) -> double {
@@ -509,13 +566,9 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
         for (int q = g; q < nf; q += NG) {
           const int f = flist[q];
           if (f < 0) continue;
-          const RowH row = rrow(cnode[f]);
           int nanc = 0;
-          const double sum = sie_pw_sum8<MAXD>([&](int i) { return rat(row, hn[i]); }, n, j, gmask, nanc);
+          const double sum = sie_pw_sum_gather<MAXD, IT, ZR>(rcx, cnode[f], hn, n, hn, n, j, gmask, &nanc);
           if (j == 0) wk += (unsigned long long)n;
-          nanc += __shfl_xor_sync(gmask, nanc, 1);
-          nanc += __shfl_xor_sync(gmask, nanc, 2);
-          nanc += __shfl_xor_sync(gmask, nanc, 4);
           const double mean = sum / (double)(n - nanc);   // np.nanmean: NaN -> 0, divide by the non-NaN count
           if (mean == mean) {
             Rec cur; cur.ord = ord_of(mean); cur.pri = (unsigned long long)(~(uint32_t)fkey[f]) << 32; cur.a = (uint32_t)q; cur.b = (uint32_t)f;
@@ -798,12 +851,7 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
           int nanc = 0;
           double sum = 0.0;
           if (len > 0) {
-            const RowH row = rrow(kn[pp]);
-            const IT* kq = kn + pp + 1;
-            sum = sie_pw_sum8<MAXD>([&](int i) { return rat(row, kq[i]); }, len, j, gmask, nanc);
-            nanc += __shfl_xor_sync(gmask, nanc, 1);
-            nanc += __shfl_xor_sync(gmask, nanc, 2);
-            nanc += __shfl_xor_sync(gmask, nanc, 4);
+            sum = sie_pw_sum_gather<MAXD, IT, ZR>(rcx, kn[pp], kn + pp + 1, len, kn, len, j, gmask, &nanc);
           }
           if (j == 0) selfbuf[sh_so[qc] + pp] = (len - nanc > 0) ? sum / (double)(len - nanc) : sie_nan();   // nanmean([]) = nan
         }
@@ -821,16 +869,7 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
           const double* base1 = D + (size_t)p * ld + (p + 1);
           const int gap = sh_xo[qc] - nb;           // element i >= nbb lives at base1[i + gap]
           int nanc = 0;
-          const double sum = sie_pw_tree<MAXD>([&](int lo, int ln) -> double {
-            if (lo + ln <= nbb || lo >= nbb) {
-              const double r = sie_pw_leaf8_contig(base1 + lo + j + (lo >= nbb ? gap : 0), ln, j, gmask);
-              if (r == r) return r;
-            }
-            return sie_pw_leaf8([&](int i) { return base1[i + (i >= nbb ? gap : 0)]; }, lo, ln, j, gmask, nanc);
-          }, len);
-          nanc += __shfl_xor_sync(gmask, nanc, 1);
-          nanc += __shfl_xor_sync(gmask, nanc, 2);
-          nanc += __shfl_xor_sync(gmask, nanc, 4);
+          const double sum = sie_pw_sum_runs<MAXD>(base1, nbb, base1 + nbb + gap, len, j, gmask, &nanc);
           if (j == 0) rowmean[u] = (len - nanc > 0) ? sum / (double)(len - nanc) : sie_nan();
         }
         __syncthreads();
@@ -840,13 +879,8 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
           const int qc = q - q0;
           const int nk = sh_koff[qc + 1] - sh_koff[qc];
           const int n = nb + nk;
-          const double* rm = rowmean + (size_t)qc * nb;
-          const double* sf = selfbuf + sh_so[qc] - nb;
           int nanc = 0;
-          const double sum = sie_pw_sum8<MAXD>([&](int i) { const double* q2 = (i < nb) ? rm + i : sf + i; return *q2; }, n, j, gmask, nanc);
-          nanc += __shfl_xor_sync(gmask, nanc, 1);
-          nanc += __shfl_xor_sync(gmask, nanc, 2);
-          nanc += __shfl_xor_sync(gmask, nanc, 4);
+          const double sum = sie_pw_sum_runs<MAXD>(rowmean + (size_t)qc * nb, nb, selfbuf + sh_so[qc], n, j, gmask, &nanc);
           if (j == 0) S.stat[S.nlist[q]] = (n - nanc > 0) ? sum / (double)(n - nanc) : sie_nan();
         }
         __syncthreads();
@@ -868,13 +902,10 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
           if (len > 0) {
             // row p of the hypothetical area best ++ k: a best row continues into k's cells, a row of k stays in k
             const bool in_best = p < nb;
-            const RowH row = rrow(in_best ? hn[p] : kn[p - nb]);
             const int nbb = in_best ? nb - 1 - p : 0;  // elements of the row inside the best area
             const IT* kq = in_best ? kn : kn + (p - nb) + 1;
-            sum = sie_pw_sum8<MAXD>([&](int i) { const IT* q = (i < nbb) ? hn + (p + 1 + i) : kq + (i - nbb); return rat(row, *q); }, len, j, gmask, nanc);
-            nanc += __shfl_xor_sync(gmask, nanc, 1);
-            nanc += __shfl_xor_sync(gmask, nanc, 2);
-            nanc += __shfl_xor_sync(gmask, nanc, 4);
+            sum = sie_pw_sum_gather<MAXD, IT, ZR>(rcx, in_best ? hn[p] : kn[p - nb], hn + (p + 1), nbb, kq, len, j, gmask,
+                                                  &nanc);
           }
           if (j == 0) rowmean[u] = (len - nanc > 0) ? sum / (double)(len - nanc) : sie_nan();   // nanmean([]) = nan
         }
@@ -885,10 +916,7 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
           const int n = sh_uoff[q - q0 + 1] - sh_uoff[q - q0];
           const double* rm = rowmean + sh_uoff[q - q0];
           int nanc = 0;
-          const double sum = sie_pw_sum8<MAXD>([&](int i) { return rm[i]; }, n, j, gmask, nanc);
-          nanc += __shfl_xor_sync(gmask, nanc, 1);
-          nanc += __shfl_xor_sync(gmask, nanc, 2);
-          nanc += __shfl_xor_sync(gmask, nanc, 4);
+          const double sum = sie_pw_sum_runs<MAXD>(rm, n, rm, n, j, gmask, &nanc);
           if (j == 0) S.stat[S.nlist[q]] = (n - nanc > 0) ? sum / (double)(n - nanc) : sie_nan();
         }
         __syncthreads();

@@ -58,6 +58,9 @@ __device__ __forceinline__ double sie_nan() { return __longlong_as_double(0x7ff8
 // Compiler fence over a register array: everything that defines v[] (the gathers) is ordered before, everything
 // that consumes it (the adds) after, so a leaf's gathers are all in flight before the first add instead of being
 // interleaved load-use-load-use (which serialises the memory round trips).
+#ifndef SIE_PW_SMALL_NQ
+#define SIE_PW_SMALL_NQ 4       // unrolled leaf variants: <= 8 * SIE_PW_SMALL_NQ elements and <= 128 (0: only the latter)
+#endif
 template <int NQ> __device__ __forceinline__ void sie_fence_regs(double (&v)[NQ]);
 template <> __device__ __forceinline__ void sie_fence_regs<1>(double (&v)[1]) { asm volatile("" : "+d"(v[0])); }
 template <> __device__ __forceinline__ void sie_fence_regs<4>(double (&v)[4]) {
@@ -114,8 +117,11 @@ __device__ __forceinline__ void sie_pw_lane8_any(Get get, int lo, int n, int ngr
                                                  double& tv, int& nan_cnt) {
   // two unrolled variants only (<= 32 elements, <= 128): every call site inlines them, and the domain-growth kernel's
   // instruction footprint matters (two CTAs in different phases share an SM's instruction cache)
-  if (ngrp <= 4) sie_pw_lane8<4>(get, lo, n, ngrp, ntail, j, acc, tv, nan_cnt);
-  else sie_pw_lane8<16>(get, lo, n, ngrp, ntail, j, acc, tv, nan_cnt);
+#if SIE_PW_SMALL_NQ > 0
+  if (ngrp <= SIE_PW_SMALL_NQ) sie_pw_lane8<SIE_PW_SMALL_NQ>(get, lo, n, ngrp, ntail, j, acc, tv, nan_cnt);
+  else
+#endif
+    sie_pw_lane8<16>(get, lo, n, ngrp, ntail, j, acc, tv, nan_cnt);
 }
 
 template <typename Get>
@@ -168,7 +174,9 @@ __device__ __forceinline__ double sie_pw_leaf8_contig_n(const double* q, int ngr
 }
 __device__ __forceinline__ double sie_pw_leaf8_contig(const double* q, int n, int j, unsigned gmask) {
   const int ngrp = (n < 8) ? 0 : (n >> 3), nt = n - 8 * ngrp;
-  if (ngrp <= 4) return sie_pw_leaf8_contig_n<4>(q, ngrp, nt, j, gmask);
+#if SIE_PW_SMALL_NQ > 0
+  if (ngrp <= SIE_PW_SMALL_NQ) return sie_pw_leaf8_contig_n<SIE_PW_SMALL_NQ>(q, ngrp, nt, j, gmask);
+#endif
   return sie_pw_leaf8_contig_n<16>(q, ngrp, nt, j, gmask);
 }
 
