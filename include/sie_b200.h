@@ -82,14 +82,16 @@ int sie_detrend_zscore(const double* fields, const int32_t* job_field, const int
  * tau      [B]; tau_sum [B]; tau_cnt [B] (int64)   -- sums are over BOTH triangles like the reference
  * shard_rank/shard_count: tile-row bi is computed by the rank with bi % shard_count == shard_rank
  *     (multi-GPU row-block split; tau is then finished by the caller after an all-reduce of sum/cnt).
- * kernel   SIE_CORR_AUTO: the 128x64 tile kernel when R is stored, the row-resident warp-specialised kernel for the
- *          tau-only pass (R == NULL); SIE_CORR_TILES / SIE_CORR_ROWS force one (both serve both modes and give the
- *          same upper triangle bit for bit).  There is no environment variable or other hidden state.
+ * kernel   SIE_CORR_AUTO: the TMA-store kernel when R is stored (the 128x64 tile kernel when Tp > ~52), the row-resident
+ *          warp-specialised kernel for the tau-only pass (R == NULL); SIE_CORR_TILES / SIE_CORR_ROWS / SIE_CORR_TMA force
+ *          one (tiles and rows serve both modes; all give the same upper triangle bit for bit).  There is no
+ *          environment variable or other hidden state.
  */
 #define SIE_CORR_AUTO 0
 #define SIE_CORR_TILES 1
 #define SIE_CORR_ROWS 2
 #define SIE_CORR_ROWS_MIRROR 3   /* rows kernel that also writes the lower triangle (debug / A-B only) */
+#define SIE_CORR_TMA 4           /* stored R only: every consumer warp's sub-tile leaves as one tensor-map bulk store (TMA) */
 int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32_t* job_T, const double* r_crit,
                  int B, int ldn, int Tp, double* R,
                  double* tile_part, size_t tile_part_bytes,

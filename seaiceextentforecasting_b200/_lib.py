@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsie_b200.so")
 
 SIE_JOB_OK, SIE_JOB_NO_NAN_CELL, SIE_JOB_FEW_AREAS, SIE_JOB_CAPACITY = 0, 1, 2, 3
-SIE_CORR_AUTO, SIE_CORR_TILES, SIE_CORR_ROWS, SIE_CORR_ROWS_MIRROR = 0, 1, 2, 3
+SIE_CORR_AUTO, SIE_CORR_TILES, SIE_CORR_ROWS, SIE_CORR_ROWS_MIRROR, SIE_CORR_TMA = 0, 1, 2, 3, 4
 ABI_VERSION = 2
 SIE_AREA_WORK = 32   # uint64 profiling counters per job (include/sie_b200.h)
 

@@ -2,6 +2,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
@@ -55,6 +57,38 @@ int sie_ensure_smem(const SieDevice* d, int slot, const void* func, size_t bytes
     return SIE_ERR_LAUNCH;
   }
   m->attr_smem[slot] = (long long)bytes;
+  return SIE_OK;
+}
+
+// Tensor map (TMA descriptor) of a batch of square FP64 matrices M [B][ld][ld]: box = box_rows x box_cols elements, no
+// swizzle.  The driver entry point is resolved once through the runtime (no link against libcuda).  `out` = 128 bytes.
+int sie_tensor_map_f64_3d(void* out, const double* base, int B, int ld, int box_cols, int box_rows) {
+  static PFN_cuTensorMapEncodeTiled encode = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    else
+      (void)cudaGetLastError();
+  });
+  if (!encode) {
+    sie_set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return SIE_ERR_UNSUPPORTED;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)ld, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(double), (cuuint64_t)ld * (cuuint64_t)ld * sizeof(double)};
+  const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult rc = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                             const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    sie_set_error("cuTensorMapEncodeTiled failed (CUresult %d; B=%d ld=%d box=%dx%d)", (int)rc, B, ld, box_rows, box_cols);
+    return SIE_ERR_LAUNCH;
+  }
   return SIE_OK;
 }
 

@@ -12,7 +12,7 @@ void sie_set_error(const char* fmt, ...);
 #define SIE_ATTR_SLOTS 16
 enum SieAttrSlot { SIE_K_DETREND = 0, SIE_K_CORR_TILES, SIE_K_CORR_ROWS_ST, SIE_K_CORR_ROWS_MIR, SIE_K_CORR_ROWS_TAU, SIE_K_AREA_ON32,
                    SIE_K_AREA_OFF32, SIE_K_AREA_ON16, SIE_K_AREA_ON16_2, SIE_K_AREA_ON32_Z, SIE_K_AREA_OFF32_Z, SIE_K_GP,
-                   SIE_K_LINKS };
+                   SIE_K_LINKS, SIE_K_CORR_TMA };
 struct SieDevice {
   volatile int ready;
   int ordinal, sm_count, max_smem_optin, smem_per_sm;
@@ -21,6 +21,7 @@ struct SieDevice {
 };
 const SieDevice* sie_device(void);                     // current device, nullptr (error set) if there is none
 int sie_ensure_smem(const SieDevice* d, int slot, const void* func, size_t bytes);
+int sie_tensor_map_f64_3d(void* out128, const double* base, int B, int ld, int box_cols, int box_rows);   // abi.cu
 
 #define SIE_CHECK_ARG(cond, msg)                 \
   do {                                           \

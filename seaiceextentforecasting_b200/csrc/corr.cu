@@ -15,6 +15,7 @@
 // the operand panels) and written as whole rows: 512-byte runs.  (k_corr_rows' stored mode still writes the mirror
 // too; it is a superset of what the readers need.)
 // Algorithmic work: N(N+1)T flop per network (upper triangle), 4 N(N+1) bytes if R is stored.
+#include <cuda.h>
 #include "common.cuh"
 
 namespace {
@@ -595,6 +596,216 @@ k_corr_rows(const double* __restrict__ z, const long long* __restrict__ prefix, 
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// k_corr_tma: the stored-R kernel.  Same contraction and warp geometry as k_corr_rows (16 consumer warps, 4 x 4, a
+// 32 x 16 sub-tile each; one producer warp; 128 x 64 tiles), but the finished tile leaves through the TMA engine:
+//   * every consumer warp stages its 32 x 16 sub-tile (32 rows of 128 B, 4 KB) in its own shared-memory box and lane 0
+//     issues ONE tensor-map bulk store (cp.async.bulk.tensor.3d, SASS UTMASTG; tensor map of R [B][ldn][ldn], box
+//     16 x 32 x 1).  The store is asynchronous: the warp goes straight to the MMAs of its next tile and only waits
+//     (cp.async.bulk.wait_group.read) before it overwrites the box again, a whole tile later.  No store warps, no CTA
+//     barrier, no second trip of the tile through the LSU pipe (k_corr_tiles stages, reads back and stores with plain
+//     st.global: store-issue bound);
+//   * the fragment -> box writes are bank-conflict free without swizzling: a quarter warp holds two rows x 64 B of each
+//     of the two 8-column blocks; even rows write their left block first, odd rows their right block, so the eight
+//     16-byte pieces of one st.shared.v2.f64 wavefront cover all 32 banks;
+//   * sub-tiles strictly below the diagonal or outside the N x N matrix are not stored; the diagonal gets NaN;
+//   * work split: chunks of TM_CHUNK consecutive tiles dealt round-robin to the CTAs.  The item table is ordered by
+//     job, and a sweep's jobs by window length, so a contiguous split (k_corr_rows) would give one CTA only long-window
+//     tiles and another only short ones; round-robin chunks give every CTA the same mix, and a chunk mostly stays
+//     inside one tile row, so the resident A panel is still reused;
+//   * the A panel is double-buffered (a new tile row's panel loads while the old one is still being consumed); the
+//     producer hands every ring slot its table entry + A buffer index through shared memory, a negative job ends the CTA.
+// tau partials: per warp and tile, same layout and summation order as k_corr_rows (k_tau_tiles folds them).
+// -------------------------------------------------------------------------------------------------
+constexpr int TM_CWARPS = 16;
+constexpr int TM_THREADS = (TM_CWARPS + 1) * 32;
+constexpr int TM_MAXS = 6;
+constexpr int TM_CHUNK = 8;
+constexpr int TM_BOX_R = 32, TM_BOX_C = 16;       // one consumer warp's sub-tile = one TMA box
+
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(TM_THREADS, 1)
+k_corr_tma(const double* __restrict__ z, const long long* __restrict__ prefix, const int4* __restrict__ table, int B,
+           int ldn, int Tp, int S, const __grid_constant__ CUtensorMap tmR, double* __restrict__ parts) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const size_t a_elems = (size_t)TILE * Tp, b_elems = (size_t)TILE_N * Tp;
+  double* sA = reinterpret_cast<double*>(smem_raw);               // [2][128][Tp]
+  double* sB = sA + 2 * a_elems;                                  // [S][64][Tp]
+  double* sC = sB + (size_t)S * b_elems;                          // [16 warps][32][16]: the TMA store boxes
+  __shared__ uint64_t full_bar[TM_MAXS], empty_bar[TM_MAXS];
+  __shared__ int4 meta0[TM_MAXS], meta1[TM_MAXS];                 // ring slot -> table entry (+ A buffer in meta1.y)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long total = prefix[B];
+  const long long G = gridDim.x, c = blockIdx.x;
+  auto item_of = [&](int k) -> long long { return ((long long)(k / TM_CHUNK) * G + c) * TM_CHUNK + (k % TM_CHUNK); };
+  if (item_of(0) >= total) return;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TM_CWARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint32_t a_bytes = (uint32_t)(a_elems * sizeof(double));
+  const uint32_t b_bytes = (uint32_t)(b_elems * sizeof(double));
+
+  if (warp == TM_CWARPS) {
+    // ---------------- producer warp (one thread)
+    if (lane != 0) return;
+    int consumed = -1;                                            // tiles 0..consumed have left the ring and their A panel
+    auto ensure = [&](int t) {
+      while (consumed < t) { ++consumed; mbar_wait(&empty_bar[consumed % S], (consumed / S) & 1); }
+    };
+    int cur_b = -1, cur_bi = -1, abuf = 1;
+    int a_last[2] = {-1, -1};                                     // last tile that reads each A buffer
+    long long item = item_of(0);
+    int4 e = table[2 * item], m = table[2 * item + 1];
+    int nl = 0;
+    while (true) {
+      const long long nitem = item_of(nl + 1);
+      const bool more = nitem < total;
+      int4 en = e, mn = m;
+      if (more) { en = table[2 * nitem]; mn = table[2 * nitem + 1]; }   // next entry in flight during the waits
+      const int s = nl % S;
+      ensure(nl - S);                                             // the ring slot is free
+      const bool new_row = (e.x != cur_b || e.y != cur_bi);
+      if (new_row) {
+        abuf ^= 1;
+        ensure(a_last[abuf]);                                     // every tile that read this A buffer is done
+        cur_b = e.x; cur_bi = e.y;
+      }
+      a_last[abuf] = nl;
+      meta0[s] = e;
+      meta1[s] = make_int4(m.x, abuf, m.z, m.w);
+      mbar_expect_tx(&full_bar[s], b_bytes + (new_row ? a_bytes : 0u));
+      if (new_row) bulk_g2s(sA + (size_t)abuf * a_elems, z + ((size_t)e.x * ldn + (size_t)e.y * TILE) * Tp, a_bytes, &full_bar[s]);
+      bulk_g2s(sB + (size_t)s * b_elems, z + ((size_t)e.x * ldn + (size_t)e.z * TILE_N) * Tp, b_bytes, &full_bar[s]);
+      ++nl;
+      if (!more) break;
+      e = en; m = mn; item = nitem;
+    }
+    const int s = nl % S;                                         // end marker
+    ensure(nl - S);
+    meta0[s] = make_int4(-1, 0, 0, 0);
+    mbar_arrive(&full_bar[s]);
+    return;
+  }
+
+  // ---------------- consumers
+  const int wr = warp >> 2, wc = warp & 3;
+  const int r8 = lane >> 2, c4 = lane & 3;
+  double* box = sC + (size_t)warp * (TM_BOX_R * TM_BOX_C);
+  bool pending = false;                                           // lane 0: a bulk store of `box` may still be reading it
+  for (int k = 0;; ++k) {
+    const int s = k % S;
+    mbar_wait(&full_bar[s], (k / S) & 1);
+    const int4 e0 = meta0[s], e1 = meta1[s];
+    if (e0.x < 0) break;
+    const long long item = item_of(k);
+    const int b = e0.x, bi = e0.y, bj = e0.z, N = e0.w, ksteps = e1.x;
+    const long long rcb = (long long)(((unsigned long long)(unsigned)e1.w << 32) | (unsigned)e1.z);
+    const double* pa = sA + (size_t)e1.y * a_elems + (size_t)(wr * 32 + r8) * Tp + c4;
+    const double* pb = sB + (size_t)s * b_elems + (size_t)(wc * 16 + r8) * Tp + c4;
+
+    double acc[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 4
+    for (int ks = 0; ks < ksteps; ++ks) {
+      double af[4], bf[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = pa[(size_t)i * 8 * Tp + ks * 4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bf[j] = pb[(size_t)j * 8 * Tp + ks * 4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);                     // this warp no longer reads the panels
+
+    const int row0 = bi * TILE, col0 = bj * TILE_N;
+    const int dk = bj - 2 * bi;                                    // 0 / 1: the two tiles of the diagonal block
+    const bool interior = dk >= 2 && row0 + TILE <= N && col0 + TILE_N <= N;
+    double lsum = 0.0;
+    int lcnt = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { acc[i][j][0] = clip_unit(acc[i][j][0]); acc[i][j][1] = clip_unit(acc[i][j][1]); }
+    if (interior) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double v0 = acc[i][j][0], v1 = acc[i][j][1];
+          const long long i0 = __double_as_longlong(v0), i1 = __double_as_longlong(v1);
+          const bool t0 = i0 > rcb && i0 <= kOneBits, t1 = i1 > rcb && i1 <= kOneBits;   // NaN images lie above 1.0's
+          lsum += t0 ? v0 : 0.0;                                   // adding +0.0 leaves a non-negative sum unchanged
+          lsum += t1 ? v1 : 0.0;
+          lcnt += (int)t0 + (int)t1;
+        }
+    } else {
+      // tiles of the diagonal block and of the ragged edge: count strictly above the diagonal, NaN on it
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gi = row0 + wr * 32 + i * 8 + r8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int gj = col0 + wc * 16 + j * 8 + 2 * c4;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double v = acc[i][j][h];
+            const bool up = gi < N && gj + h < N && (dk >= 2 || gj + h > gi);
+            const long long iv = __double_as_longlong(v);
+            const bool t = up && iv > rcb && iv <= kOneBits;
+            lsum += t ? v : 0.0;
+            lcnt += (int)t;
+            if (dk < 2 && gj + h == gi) acc[i][j][h] = sie_nan();
+          }
+        }
+      }
+    }
+    // ---- the sub-tile leaves through the TMA engine (skipped when it lies strictly below the diagonal or outside N)
+    const int sr0 = row0 + wr * 32, sc0 = col0 + wc * 16;
+    if (sc0 + TM_BOX_C - 1 >= sr0 && sr0 < N && sc0 < N) {
+      if (lane == 0 && pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      const bool odd = r8 & 1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double* rowp = box + (size_t)(i * 8 + r8) * TM_BOX_C + 2 * c4;
+        const double2 left = make_double2(acc[i][0][0], acc[i][0][1]), right = make_double2(acc[i][1][0], acc[i][1][1]);
+        // even rows: left block then right block; odd rows the other way round (bank-conflict free wavefronts)
+        *reinterpret_cast<double2*>(rowp + (odd ? 8 : 0)) = odd ? right : left;
+        *reinterpret_cast<double2*>(rowp + (odd ? 0 : 8)) = odd ? left : right;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tmR, box, sc0, sr0, b);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        pending = true;
+      }
+    }
+    double lc = (double)lcnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+      lc += __shfl_xor_sync(0xffffffffu, lc, o);
+    }
+    if (lane == 0) *reinterpret_cast<double2*>(parts + (item * TM_CWARPS + warp) * 2) = make_double2(lsum, lc);
+  }
+  if (lane == 0 && pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores done before the CTA exits
+}
+
 // one thread per tile: the 16 warp partials of k_corr_rows in warp order, doubled (both triangles) -> one pair per tile
 __global__ void k_tau_tiles(const double* __restrict__ parts, const long long* __restrict__ prefix, int B,
                             double* __restrict__ tile_pair) {
@@ -721,7 +932,7 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
                             size_t tile_part_bytes, double* tau_sum, int64_t* tau_cnt, double* tau,
                             int shard_rank, int shard_count, int kernel, void* stream) {
   SIE_CHECK_ARG(kernel == SIE_CORR_AUTO || kernel == SIE_CORR_TILES || kernel == SIE_CORR_ROWS ||
-                    kernel == SIE_CORR_ROWS_MIRROR, "unknown kernel choice");
+                    kernel == SIE_CORR_ROWS_MIRROR || kernel == SIE_CORR_TMA, "unknown kernel choice");
   SIE_CHECK_ARG(z && n_nodes && job_T && r_crit && tile_part && tau_sum && tau_cnt && tau, "null pointer");
   SIE_CHECK_ARG(B > 0 && ldn > 0 && (ldn % TILE) == 0, "ldn must be a positive multiple of 128");
   SIE_CHECK_ARG(Tp >= 4 && (Tp % 4) == 0, "Tp must be a multiple of 4");
@@ -764,8 +975,30 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
   // default: rows kernel for the tau-only pass (25.2 vs 22.6 TFLOP/s at 25 km), tile kernel when R is stored (0.277 vs
   // 0.325 ms on 24 57x57 networks, tools/corr_ab.py: the rows kernel's staging trip through shared memory costs more
   // than its resident A panel and its store warps save)
+  // stored R: the TMA-store kernel (tensor-map bulk stores straight from the consumer warps) whenever its shared memory
+  // fits: two A panels + the 64-KB store boxes + >= 2 ring stages
+  const size_t tm_fixed = 2 * (size_t)TILE * Tp * sizeof(double) + (size_t)TM_CWARPS * TM_BOX_R * TM_BOX_C * sizeof(double);
+  int tmS = (size_t)max_optin < tm_fixed + 512 ? 0 : (int)(((size_t)max_optin - 512 - tm_fixed) / rw_stage);
+  if (tmS > TM_MAXS) tmS = TM_MAXS;
+  const bool use_tma = R != nullptr && tmS >= 2 && (kernel == SIE_CORR_AUTO || kernel == SIE_CORR_TMA);
+  if (kernel == SIE_CORR_TMA && !use_tma) {
+    sie_set_error("sie_corr_tau: SIE_CORR_TMA needs a stored R and Tp <= ~52 (Tp = %d)", Tp);
+    return SIE_ERR_UNSUPPORTED;
+  }
   const bool want_rows = kernel == SIE_CORR_AUTO ? (R == nullptr) : (kernel != SIE_CORR_TILES);
-  const bool use_rows = S >= 2 && want_rows;
+  const bool use_rows = S >= 2 && want_rows && !use_tma;
+  if (use_tma) {
+    alignas(64) CUtensorMap tm;
+    if (int rc = sie_tensor_map_f64_3d(&tm, R, B, ldn, TM_BOX_C, TM_BOX_R)) return rc;
+    const size_t tsmem = tm_fixed + (size_t)tmS * rw_stage;
+    if (int rc = sie_ensure_smem(dev, SIE_K_CORR_TMA, (const void*)k_corr_tma, tsmem)) return rc;
+    const long long chunks = (max_items + TM_CHUNK - 1) / TM_CHUNK;
+    const int grid = (int)(chunks < sms ? chunks : sms);
+    k_corr_tma<<<grid, TM_THREADS, tsmem, st>>>(z, prefix, table, B, ldn, Tp, tmS, tm, parts);
+    SIE_CHECK_LAUNCH();
+    k_tau_tiles<<<(unsigned)((max_items + 255) / 256), 256, 0, st>>>(parts, prefix, B, tile_pair);
+    SIE_CHECK_LAUNCH();
+  } else
   if (use_rows) {
     const size_t rsmem = rw_fixed + (size_t)S * rw_stage;
     const int grid = (int)(max_items < sms ? max_items : sms);

@@ -205,8 +205,8 @@ def test_row_sharded_tau_matches_unsharded_and_numpy(lib_built):
 @pytest.mark.parametrize("X,Y,Ts,latlon", [(20, 22, [7, 12, 30, 42], False), (57, 57, [7, 25, 42], False),
                                            (26, 90, [9, 42], True), (81, 81, [33], False)])
 def test_both_correlation_kernels_agree(lib_built, X, Y, Ts, latlon):
-    """`sie_corr_tau` has two kernels (csrc/corr.cu): the tile kernel (default when R is stored) and the row-resident,
-    warp-specialised one (default for the tau-only pass).  Either can serve either mode (the `kernel` argument): the stored
+    """`sie_corr_tau` has three kernels (csrc/corr.cu): the TMA-store kernel (default when R is stored), the tile kernel
+    (its fallback for very long windows) and the row-resident, warp-specialised one (default for the tau-only pass).  Either can serve either mode (the `kernel` argument): the stored
     upper triangle of R (what every reader addresses, R[min][max]) must be bitwise identical with a NaN diagonal and no
     element left unwritten, the count identical and tau within 1e-12; SIE_CORR_ROWS_MIRROR also writes the mirror image, which
     must equal it bitwise; R matches numpy's corrcoef of the detrended nodes to 1e-9 (ComplexNetworks.py:34-35)."""
@@ -225,19 +225,21 @@ def test_both_correlation_kernels_agree(lib_built, X, Y, Ts, latlon):
     N = eng.n_nodes.cpu().numpy()
     out = {}
     from seaiceextentforecasting_b200 import _lib
-    for kern, kid in (("tiles", _lib.SIE_CORR_TILES), ("rows", _lib.SIE_CORR_ROWS), ("mirror", _lib.SIE_CORR_ROWS_MIRROR)):
+    for kern, kid in (("tiles", _lib.SIE_CORR_TILES), ("rows", _lib.SIE_CORR_ROWS), ("mirror", _lib.SIE_CORR_ROWS_MIRROR),
+                      ("tma", _lib.SIE_CORR_TMA)):
         eng.R.fill_(-7.0)
         eng.corr_tau(rc, store_R=True, kernel=kid)
         torch.cuda.synchronize()
         Rs = [eng.R[b, :N[b], :N[b]].cpu().numpy().copy() for b in range(B)]
         stored = (eng.tau.cpu().numpy().copy(), eng.tau_cnt.cpu().numpy().copy())
-        eng.corr_tau(rc, store_R=False, kernel=kid)
+        eng.corr_tau(rc, store_R=False, kernel=_lib.SIE_CORR_ROWS if kern == "tma" else kid)   # tma: stored mode only
         torch.cuda.synchronize()
         out[kern] = (Rs, stored, (eng.tau.cpu().numpy().copy(), eng.tau_cnt.cpu().numpy().copy()))
     for b in range(B):
-        a, c, f = out["tiles"][0][b], out["rows"][0][b], out["mirror"][0][b]
+        a, c, f, t = out["tiles"][0][b], out["rows"][0][b], out["mirror"][0][b], out["tma"][0][b]
         iu = np.triu_indices(a.shape[0], 1)
-        assert np.array_equal(a[iu], c[iu]) and np.array_equal(a[iu], f[iu])
+        assert np.array_equal(a[iu], c[iu]) and np.array_equal(a[iu], f[iu]) and np.array_equal(a[iu], t[iu])
+        assert np.isnan(np.diag(t)).all()
         assert not (a[iu] == -7.0).any() and np.isfinite(a[iu]).all()
         assert np.isnan(np.diag(a)).all() and np.isnan(np.diag(c)).all() and np.isnan(np.diag(f)).all()
         assert np.array_equal(f, f.T, equal_nan=True) and not (f == -7.0).any()       # the mirror-writing variant
@@ -250,6 +252,7 @@ def test_both_correlation_kernels_agree(lib_built, X, Y, Ts, latlon):
     for mode in (1, 2):
         assert np.array_equal(out["tiles"][mode][1], out["rows"][mode][1])
         np.testing.assert_allclose(out["tiles"][mode][0], out["rows"][mode][0], rtol=1e-12)
+    assert np.array_equal(out["tma"][1][1], out["rows"][1][1]) and np.array_equal(out["tma"][1][0], out["rows"][1][0])
     assert np.array_equal(out["rows"][1][1], out["rows"][2][1])
     np.testing.assert_allclose(out["rows"][1][0], out["rows"][2][0], rtol=1e-12)
 

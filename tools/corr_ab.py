@@ -6,7 +6,7 @@ from seaiceextentforecasting_b200 import _lib
 from seaiceextentforecasting_b200.engine import NetworkBatch, h2d, r_crit_ttest
 
 KERNELS = (("tiles", _lib.SIE_CORR_TILES), ("rows", _lib.SIE_CORR_ROWS))
-STORED = KERNELS + (("mirror", _lib.SIE_CORR_ROWS_MIRROR),)
+STORED = KERNELS + (("mirror", _lib.SIE_CORR_ROWS_MIRROR), ("tma", _lib.SIE_CORR_TMA))
 
 
 def timed(fn, reps=5):
@@ -45,6 +45,8 @@ def stored(X, Y, Ts, latlon=False):
         same = np.array_equal(a[iu], c[iu])            # the tile kernel stores the upper triangle only
         f = out["mirror"][0][b]
         sym = np.array_equal(f, f.T, equal_nan=True) and np.array_equal(f[iu], a[iu])     # the mirror-writing variant
+        t = out["tma"][0][b]
+        assert np.array_equal(t[iu], a[iu]) and np.isnan(np.diag(t)).all(), "tma kernel differs"
         print(f"  job {b}: R bitwise equal {same}, symmetric {sym}, diag NaN {np.isnan(np.diag(c)).all()}, untouched {(c == -7.0).sum()}")
         assert same and sym
     print("  tau rel diff", np.abs(out["tiles"][1] - out["rows"][1]).max() / np.abs(out["tiles"][1]).max(), "cnt equal", np.array_equal(out["tiles"][2], out["rows"][2]))
@@ -82,7 +84,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "tau":
         tau_only(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "stored":
-        stored(57, 57, [7 + (i * 35) // 23 for i in range(24)]); sys.exit(0)
+        stored(57, 57, [7 + (i * 35) // 23 for i in range(24)])
+        stored(57, 57, sorted([7 + i % 36 for i in range(576)], reverse=True)); sys.exit(0)     # 4 members x 4 inits of the sweep
     stored(20, 22, [7, 12, 30, 42])
     stored(57, 57, [7 + (i * 35) // 23 for i in range(24)])
     stored(26, 90, [9, 42], latlon=True)
