@@ -217,6 +217,10 @@ __device__ SIE_RUNS_ATTR double sie_pw_sum_runs(const double* __restrict__ a, in
     if (lo + ln <= na || lo >= na) {
       const double r = sie_pw_leaf8_contig((lo >= na ? b + (lo - na) : a + lo) + j, ln, j, gmask);
       if (r == r) return r;
+    } else {     // the leaf straddles the two runs: lane j's first ks full-group elements lie in run a
+      const int rem = na - lo - j;
+      const double r = sie_pw_leaf8_two(a + lo + j, b + (lo + j - na), rem > 0 ? (rem + 7) >> 3 : 0, ln, j, gmask);
+      if (r == r) return r;
     }
     return sie_pw_leaf8([&](int i) { return i < na ? a[i] : b[i - na]; }, lo, ln, j, gmask, nanc);
   }, n);

@@ -181,6 +181,43 @@ __device__ __forceinline__ double sie_pw_leaf8_contig(const double* q, int n, in
   return sie_pw_leaf8_contig_n<16>(q, ngrp, nt, j, gmask);
 }
 
+// One leaf (n <= 128) that STRADDLES two contiguous runs: elements below the switch come from run a, the rest from run b.
+// qa = address of this lane's element of the leaf if it lay in run a, qb = the same for run b; ks = number of this lane's
+// full-group elements (k = 0, 1, ...) that lie in run a.  Per element one pointer select + an immediate-offset load
+// (the generic getter path costs ~4x the instructions); no NaN screening, the caller redoes a NaN result.  Reads up to
+// 135 elements past the end of run b (masked out of the sum).
+template <int NQ>
+__device__ __forceinline__ double sie_pw_leaf8_two_n(const double* qa, const double* qb, int ks, int ngrp, int nt, int j,
+                                                     unsigned gmask) {
+  double v[NQ];
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) v[k] = ((k < ks) ? qa : qb)[8 * k];
+  double t[1];
+  t[0] = ((ngrp < ks) ? qa : qb)[8 * ngrp];
+  sie_fence_regs<NQ>(v);
+  sie_fence_regs<1>(t);
+  double r = v[0];
+#pragma unroll
+  for (int k = 1; k < NQ; ++k) if (k < ngrp) r = __dadd_rn(r, v[k]);
+  double res = 0.0;
+  if (ngrp > 0) {
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 1));
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 2));
+    r = __dadd_rn(r, __shfl_xor_sync(gmask, r, 4));
+    res = r;
+  }
+  const double tv = (j < nt) ? t[0] : 0.0;
+  res = sie_add_tail8(res, tv, nt, gmask);
+  return res;
+}
+__device__ __forceinline__ double sie_pw_leaf8_two(const double* qa, const double* qb, int ks, int n, int j, unsigned gmask) {
+  const int ngrp = (n < 8) ? 0 : (n >> 3), nt = n - 8 * ngrp;
+#if SIE_PW_SMALL_NQ > 0
+  if (ngrp <= SIE_PW_SMALL_NQ) return sie_pw_leaf8_two_n<SIE_PW_SMALL_NQ>(qa, qb, ks, ngrp, nt, j, gmask);
+#endif
+  return sie_pw_leaf8_two_n<16>(qa, qb, ks, ngrp, nt, j, gmask);
+}
+
 // numpy's pairwise recursion pairwise(lo,n) = pairwise(lo,n2) + pairwise(lo+n2,n-n2), n2 = n/2 - (n/2)%8, over leaves of
 // <= 128 elements, walked left to right without a memory stack: the path from the root is a bit mask (bit d = "right
 // child at depth d+1"), node bounds are recomputed from the root (<= 16 integer steps), and the pending left-sibling

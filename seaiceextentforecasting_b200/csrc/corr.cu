@@ -16,6 +16,7 @@
 // too; it is a superset of what the readers need.)
 // Algorithmic work: N(N+1)T flop per network (upper triangle), 4 N(N+1) bytes if R is stored.
 #include <cuda.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -631,7 +632,7 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_
 
 __global__ void __launch_bounds__(TM_THREADS, 1)
 k_corr_tma(const double* __restrict__ z, const long long* __restrict__ prefix, const int4* __restrict__ table, int B,
-           int ldn, int Tp, int S, const __grid_constant__ CUtensorMap tmR, double* __restrict__ parts) {
+           int ldn, int Tp, int S, int chunk, const __grid_constant__ CUtensorMap tmR, double* __restrict__ parts) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const size_t a_elems = (size_t)TILE * Tp, b_elems = (size_t)TILE_N * Tp;
   double* sA = reinterpret_cast<double*>(smem_raw);               // [2][128][Tp]
@@ -643,7 +644,7 @@ k_corr_tma(const double* __restrict__ z, const long long* __restrict__ prefix, c
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long total = prefix[B];
   const long long G = gridDim.x, c = blockIdx.x;
-  auto item_of = [&](int k) -> long long { return ((long long)(k / TM_CHUNK) * G + c) * TM_CHUNK + (k % TM_CHUNK); };
+  auto item_of = [&](int k) -> long long { const int q = k / chunk; return ((long long)q * G + c) * chunk + (k - q * chunk); };
   if (item_of(0) >= total) return;
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TM_CWARPS); }
@@ -992,9 +993,14 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
     if (int rc = sie_tensor_map_f64_3d(&tm, R, B, ldn, TM_BOX_C, TM_BOX_R)) return rc;
     const size_t tsmem = tm_fixed + (size_t)tmS * rw_stage;
     if (int rc = sie_ensure_smem(dev, SIE_K_CORR_TMA, (const void*)k_corr_tma, tsmem)) return rc;
-    const long long chunks = (max_items + TM_CHUNK - 1) / TM_CHUNK;
+    int chunk = TM_CHUNK;
+#ifdef SIE_TUNE
+    if (const char* e = getenv("SIE_TM_CHUNK")) chunk = atoi(e);
+    if (const char* e = getenv("SIE_TM_S")) { const int v = atoi(e); if (v >= 2 && v < tmS) tmS = v; }
+#endif
+    const long long chunks = (max_items + chunk - 1) / chunk;
     const int grid = (int)(chunks < sms ? chunks : sms);
-    k_corr_tma<<<grid, TM_THREADS, tsmem, st>>>(z, prefix, table, B, ldn, Tp, tmS, tm, parts);
+    k_corr_tma<<<grid, TM_THREADS, tsmem, st>>>(z, prefix, table, B, ldn, Tp, tmS, chunk, tm, parts);
     SIE_CHECK_LAUNCH();
     k_tau_tiles<<<(unsigned)((max_items + 255) / 256), 256, 0, st>>>(parts, prefix, B, tile_pair);
     SIE_CHECK_LAUNCH();

@@ -80,7 +80,24 @@ def tau_only():
     print("  tau_sum rel diff tiles/rows", abs(res["tiles"][0] - res["rows"][0]) / abs(res["tiles"][0]))
 
 
+def tma_only():
+    """time the stored-R default alone on the 4-member sweep shape (chunk / ring depth tuning in a SIE_TUNE build)"""
+    X = Y = 57
+    Ts = sorted([7 + i % 36 for i in range(576)], reverse=True); B = len(Ts); T = max(Ts); C = X * Y
+    data, _ = syn.make_field(X, Y, T, 11)
+    n_upper = int((~np.isnan(data).all(axis=2)).sum())
+    eng = NetworkBatch(X, Y, T, B, latlon=False, n_upper=n_upper, keep_R=True, max_areas=8)
+    fields = h2d(data.reshape(1, C, T))
+    jf = torch.zeros(B, dtype=torch.int32, device="cuda"); jT = torch.tensor(Ts, dtype=torch.int32, device="cuda")
+    rc = h2d(np.array([r_crit_ttest(t, 0.01) for t in Ts]))
+    eng.detrend_zscore(fields, jf, jT, True); torch.cuda.synchronize()
+    ms = timed(lambda: eng.corr_tau(rc, store_R=True, kernel=_lib.SIE_CORR_TMA))
+    print(f"tma chunk={os.environ.get('SIE_TM_CHUNK')} S={os.environ.get('SIE_TM_S')}: {ms:.3f} ms")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "tma":
+        tma_only(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "tau":
         tau_only(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "stored":
