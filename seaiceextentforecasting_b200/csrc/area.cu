@@ -233,9 +233,12 @@ __device__ SIE_RUNS_ATTR double sie_pw_sum_runs(const double* __restrict__ a, in
 
 struct RCtx { const double* R; int ldn, Tp, kT; };    // where correlations come from: R (stride ldn) or z rows (stride Tp)
 __device__ double sie_zcorr(const double* __restrict__ za, const double* __restrict__ zc, int kT, bool diag);
-template <bool ZR>
+// W32: ldn^2 < 2^31 (16-bit index variants), so the element offset min*ldn + max is 32-bit arithmetic: one IMAD + two
+// min/max instead of 64-bit selects and multiplies at every gather site (hot-path instructions AND code footprint)
+template <bool ZR, bool W32>
 __device__ __forceinline__ double sie_rat(const RCtx& cx, int a, int c) {
   if constexpr (ZR) return sie_zcorr(cx.R + (size_t)a * cx.Tp, cx.R + (size_t)c * cx.Tp, cx.kT, a == c);
+  else if constexpr (W32) return SIE_RLOAD(cx.R + (unsigned)(min(a, c) * cx.ldn + max(a, c)));
   else return (c >= a) ? SIE_RLOAD(cx.R + (size_t)a * cx.ldn + c) : SIE_RLOAD(cx.R + (size_t)c * cx.ldn + a);   // R[min][max]
 }
 // numpy pairwise sum of the correlations of node `rown` with the nodes ia[0..na) ++ ib[0..n-na) (index lists in shared
@@ -245,7 +248,7 @@ template <int MAXD, typename IT, bool ZR>
 __device__ SIE_GATHER_ATTR double sie_pw_sum_gather(RCtx cx, int rown, const IT* ia, int na, const IT* ib, int n, int j,
                                                  unsigned gmask, int* nan_out) {
   int nanc = 0;
-  const double sum = sie_pw_sum8<MAXD>([&](int i) { return sie_rat<ZR>(cx, rown, (int)(i < na ? ia[i] : ib[i - na])); },
+  const double sum = sie_pw_sum8<MAXD>([&](int i) { return sie_rat<ZR, sizeof(IT) == 2>(cx, rown, (int)(i < na ? ia[i] : ib[i - na])); },
                                        n, j, gmask, nanc);
   nanc += __shfl_xor_sync(gmask, nanc, 1);
   nanc += __shfl_xor_sync(gmask, nanc, 2);
@@ -383,6 +386,7 @@ k_area_level(const double* __restrict__ Rall, const int32_t* __restrict__ job_T,
   auto rrow = [&](int a) -> RowH { RowH h; h.n = a; h.p = R + (size_t)a * (ZR ? Tp : ldn); return h; };
   auto rat = [&](const RowH& h, int c) -> double {
     if constexpr (ZR) return sie_zcorr(h.p, R + (size_t)c * Tp, kT, h.n == c);
+    else if constexpr (sizeof(IT) == 2) return SIE_RLOAD(R + (unsigned)(min(c, h.n) * ldn + max(c, h.n)));   // 32-bit offsets
     else return (c >= h.n) ? SIE_RLOAD(h.p + c) : SIE_RLOAD(R + (size_t)c * ldn + h.n);   // upper triangle stored: R[min][max]
   };
   const double* sten = stencil_all + (size_t)b * ldn * 4;
