@@ -489,13 +489,15 @@ def run_ours(args):
     clocks = sampler.stop(t_wall0, t_wall1)
     # per-stage device times (for the roofline block): same work, every stage alone on one stream so that events
     # bracket exactly one stage with nothing else on the GPU; not part of the headline timing
-    marks_all = []
+    # (minimum over the passes, each pass synchronised: a host-side stall between two launches of a pass - e.g. the
+    # clock poller's last nvidia-smi call holding the driver - would otherwise be booked to whatever stage it hit)
+    stage_ms = {}
     for _ in range(min(args.steps, 5)):
         marks = []
         sw.compute(marks, waves=0)
-        marks_all.append(marks)
-    sync_all()
-    stage_ms = stage_times(marks_all, len(marks_all))
+        sync_all()
+        for k, v in stage_times([marks], 1).items():
+            stage_ms[k] = min(stage_ms.get(k, v), v)
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     nf = torch.tensor([float(sw.n_forecasts)], dtype=torch.float64, device="cuda")
     per_rank_ms = [dev_ms / args.steps]
