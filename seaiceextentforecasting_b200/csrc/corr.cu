@@ -16,7 +16,6 @@
 // too; it is a superset of what the readers need.)
 // Algorithmic work: N(N+1)T flop per network (upper triangle), 4 N(N+1) bytes if R is stored.
 #include <cuda.h>
-#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -632,7 +631,8 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_
 
 __global__ void __launch_bounds__(TM_THREADS, 1)
 k_corr_tma(const double* __restrict__ z, const long long* __restrict__ prefix, const int4* __restrict__ table, int B,
-           int ldn, int Tp, int S, int chunk, const __grid_constant__ CUtensorMap tmR, double* __restrict__ parts) {
+           int ldn, int Tp, int S, const __grid_constant__ CUtensorMap tmR, double* __restrict__ parts) {
+  constexpr int chunk = TM_CHUNK;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const size_t a_elems = (size_t)TILE * Tp, b_elems = (size_t)TILE_N * Tp;
   double* sA = reinterpret_cast<double*>(smem_raw);               // [2][128][Tp]
@@ -701,9 +701,12 @@ k_corr_tma(const double* __restrict__ z, const long long* __restrict__ prefix, c
   const int r8 = lane >> 2, c4 = lane & 3;
   double* box = sC + (size_t)warp * (TM_BOX_R * TM_BOX_C);
   bool pending = false;                                           // lane 0: a bulk store of `box` may still be reading it
+  int s = -1;
+  uint32_t ring_phase = 1u;                                       // parity of the current pass over the ring
   for (int k = 0;; ++k) {
-    const int s = k % S;
-    mbar_wait(&full_bar[s], (k / S) & 1);
+    if (++s == S) s = 0;
+    if (s == 0) ring_phase ^= 1u;
+    mbar_wait(&full_bar[s], ring_phase);
     const int4 e0 = meta0[s], e1 = meta1[s];
     if (e0.x < 0) break;
     const long long item = item_of(k);
@@ -737,10 +740,21 @@ k_corr_tma(const double* __restrict__ z, const long long* __restrict__ prefix, c
     const bool interior = dk >= 2 && row0 + TILE <= N && col0 + TILE_N <= N;
     double lsum = 0.0;
     int lcnt = 0;
+    {   // clip to [-1, 1] (np.clip keeps NaN): ONE branch per tile on the largest |high word| instead of one per value
+      unsigned hmax = 0u;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) { acc[i][j][0] = clip_unit(acc[i][j][0]); acc[i][j][1] = clip_unit(acc[i][j][1]); }
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) hmax = max(hmax, (unsigned)__double2hiint(acc[i][j][h]) & 0x7fffffffu);
+      if (hmax >= 0x3ff00000u) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) { acc[i][j][0] = clip_unit(acc[i][j][0]); acc[i][j][1] = clip_unit(acc[i][j][1]); }
+      }
+    }
     if (interior) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -993,14 +1007,9 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
     if (int rc = sie_tensor_map_f64_3d(&tm, R, B, ldn, TM_BOX_C, TM_BOX_R)) return rc;
     const size_t tsmem = tm_fixed + (size_t)tmS * rw_stage;
     if (int rc = sie_ensure_smem(dev, SIE_K_CORR_TMA, (const void*)k_corr_tma, tsmem)) return rc;
-    int chunk = TM_CHUNK;
-#ifdef SIE_TUNE
-    if (const char* e = getenv("SIE_TM_CHUNK")) chunk = atoi(e);
-    if (const char* e = getenv("SIE_TM_S")) { const int v = atoi(e); if (v >= 2 && v < tmS) tmS = v; }
-#endif
-    const long long chunks = (max_items + chunk - 1) / chunk;
+    const long long chunks = (max_items + TM_CHUNK - 1) / TM_CHUNK;     // chunk sizes 2..64 and ring depths 2..6 time the same
     const int grid = (int)(chunks < sms ? chunks : sms);
-    k_corr_tma<<<grid, TM_THREADS, tsmem, st>>>(z, prefix, table, B, ldn, Tp, tmS, chunk, tm, parts);
+    k_corr_tma<<<grid, TM_THREADS, tsmem, st>>>(z, prefix, table, B, ldn, Tp, tmS, tm, parts);
     SIE_CHECK_LAUNCH();
     k_tau_tiles<<<(unsigned)((max_items + 255) / 256), 256, 0, st>>>(parts, prefix, B, tile_pair);
     SIE_CHECK_LAUNCH();
