@@ -133,10 +133,27 @@ __device__ __noinline__ void cta_gemm(double* __restrict__ Cm, int ldc, const do
     const int t = step / kc, c = step - t * kc;
     if (step + 1 < nsteps) gload(step + 1);
     if (c == 0) {
+      if (mode) {
+        // C -= A*B: the accumulator starts from C (its L2 round trip overlaps this step's MMAs being set up instead of
+        // sitting exposed in the epilogue) and the A fragments are negated
+        const int ti = t / tn, tj = t - ti * tn;
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < 2; ++i) {
+          const int gr = ti * 64 + wr * 16 + i * 8 + (lane >> 2);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
+          for (int jj = 0; jj < 4; ++jj) {
+            const int gc = tj * 64 + wc * 32 + jj * 8 + 2 * (lane & 3);
+            const double* pc = Cm + (size_t)gr * ldc + gc;
+            acc[i][jj][0] = (gr < m && gc < n2) ? pc[0] : 0.0;
+            acc[i][jj][1] = (gr < m && gc + 1 < n2) ? pc[1] : 0.0;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
+      }
     }
     const double* as = sm.As[bufi] + (wr * 16 + (lane >> 2)) * LDA_S + (lane & 3);
     const double* bs = sm.Bs[bufi] + (lane & 3) * LDB_S + wc * 32 + (lane >> 2);
@@ -144,7 +161,7 @@ __device__ __noinline__ void cta_gemm(double* __restrict__ Cm, int ldc, const do
     for (int ks = 0; ks < KC / 4; ++ks) {
       double af[2], bf[4];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) af[i] = as[i * 8 * LDA_S + ks * 4];
+      for (int i = 0; i < 2; ++i) af[i] = mode ? -as[i * 8 * LDA_S + ks * 4] : as[i * 8 * LDA_S + ks * 4];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) bf[jj] = bs[ks * 4 * LDB_S + jj * 8];
 #pragma unroll
@@ -162,8 +179,8 @@ __device__ __noinline__ void cta_gemm(double* __restrict__ Cm, int ldc, const do
         for (int jj = 0; jj < 4; ++jj) {
           const int gc = tj * 64 + wc * 32 + jj * 8 + 2 * (lane & 3);
           double* pc = Cm + (size_t)gr * ldc + gc;
-          if (gc < n2) pc[0] = mode ? pc[0] - acc[i][jj][0] : acc[i][jj][0];
-          if (gc + 1 < n2) pc[1] = mode ? pc[1] - acc[i][jj][1] : acc[i][jj][1];
+          if (gc < n2) pc[0] = acc[i][jj][0];
+          if (gc + 1 < n2) pc[1] = acc[i][jj][1];
         }
       }
     }
@@ -186,15 +203,36 @@ __device__ __noinline__ double cta_norm1(const double* __restrict__ A, int ld, i
 // exact || (scale*|A|)^p ||_1 by p transposed mat-vecs on the ones vector (non-negative matrix)
 __device__ __noinline__ double cta_absnorm_power(const double* __restrict__ A, int ld, int np_, double scale, int p,
                                     double* __restrict__ v0, double* __restrict__ v1, Smem& sm) {
+  // every thread works: column j's dot product is split over `parts` row slices (thread = (slice, column)), the slice
+  // partials go through shared memory (the GEMM staging buffer, idle here) and are added in slice order
+  const int parts = (np_ <= GT / 8) ? 8 : (np_ <= GT / 4) ? 4 : (np_ <= GT / 2) ? 2 : 1;
+  double* part = &sm.As[0][0];                       // [parts][np_] <= GT doubles
+  const int jc = threadIdx.x % np_, sl = threadIdx.x / np_;
   for (int j = threadIdx.x; j < np_; j += GT) v0[j] = 1.0;
   __syncthreads();
   double* src = v0;
   double* dst = v1;
   for (int it = 0; it < p; ++it) {
-    for (int j = threadIdx.x; j < np_; j += GT) {
-      double s = 0.0;
-      for (int i = 0; i < np_; ++i) s = fma(scale * fabs(A[(size_t)i * ld + j]), src[i], s);
-      dst[j] = s;
+    if (parts > 1) {
+      if (sl < parts) {
+        double s = 0.0;
+#pragma unroll 4
+        for (int i = sl; i < np_; i += parts) s = fma(scale * fabs(A[(size_t)i * ld + jc]), src[i], s);
+        part[sl * np_ + jc] = s;
+      }
+      __syncthreads();
+      if (threadIdx.x < np_) {
+        double s = part[threadIdx.x];
+        for (int q = 1; q < parts; ++q) s += part[q * np_ + threadIdx.x];
+        dst[threadIdx.x] = s;
+      }
+    } else {
+      for (int j = threadIdx.x; j < np_; j += GT) {
+        double s = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < np_; ++i) s = fma(scale * fabs(A[(size_t)i * ld + j]), src[i], s);
+        dst[j] = s;
+      }
     }
     __syncthreads();
     double* t = src; src = dst; dst = t;
@@ -216,6 +254,7 @@ __device__ __forceinline__ int ell_of(double t, double normA, int idx, int m) {
 // dst = c0*I + c1*P1 + c2*P2 + c3*P3 (+ add) ; any pointer may be null
 __device__ __noinline__ void cta_lincomb(double* __restrict__ dst, int ld, int np_, double cI, const double* P1, double c1,
                             const double* P2, double c2, const double* P3, double c3, const double* add) {
+#pragma unroll 4
   for (int idx = threadIdx.x; idx < np_ * np_; idx += GT) {
     const int i = idx / np_, jj = idx - i * np_;
     const size_t o = (size_t)i * ld + jj;
@@ -414,6 +453,7 @@ __device__ __noinline__ double* cta_expm(double** buf, int ld, int np_, double* 
     s += ell_of(cta_absnorm_power(A, ld, np_, sc, 27, v0, v1, sm), normA * sc, 4, 13);
     if (s > 2000) s = 2000;
     const double s1 = ldexp(1.0, -s), s2 = ldexp(1.0, -2 * s), s4 = ldexp(1.0, -4 * s), s6 = ldexp(1.0, -6 * s);
+#pragma unroll 2
     for (int idx = threadIdx.x; idx < np_ * np_; idx += GT) {
       const int i = idx / np_, jj = idx - i * np_; const size_t o = (size_t)i * ld + jj;
       A[o] *= s1; A2[o] *= s2; A4[o] *= s4; A6[o] *= s6;
@@ -428,6 +468,7 @@ __device__ __noinline__ double* cta_expm(double** buf, int ld, int np_, double* 
     cta_lincomb(V, ld, np_, kB13[0], A6, kB13[6], A4, kB13[4], A2, kB13[2], B6);
   }
   // P = V - U -> B5 ; Q = V + U -> B6 ; solve P X = Q
+#pragma unroll 4
   for (int idx = threadIdx.x; idx < np_ * np_; idx += GT) {
     const int i = idx / np_, jj = idx - i * np_; const size_t o = (size_t)i * ld + jj;
     const double u = U[o], vv = V[o];
