@@ -34,21 +34,24 @@ __global__ void __launch_bounds__(DT_CELLS) k_detrend_cells(
   const double* src = fields + ((size_t)job_field[b] * C + c0) * Tstride;
   double* dst = dt + ((size_t)b * C + c0) * Tstride;
   const int tid = threadIdx.x;
-  // the CTA's series are one contiguous run of nc * Tstride doubles: flat coalesced copy, 8 loads in flight per thread
-  // before the first shared-memory store (a load -> store loop pays one memory round trip per iteration)
-  const int total = nc * Tstride, pad = ld - Tstride;
+  // only the job's window (the first T samples of every series) is staged: runs of T doubles out of rows of Tstride,
+  // flat index -> (cell, t) by a multiply-high with the rounded-up reciprocal of T (exact for idx < 2^16 * T), 8 loads in
+  // flight per thread before the first shared-memory store (a load -> store loop pays one memory round trip per iteration)
+  const int total = nc * T;
+  const unsigned rcpT = 0xffffffffu / (unsigned)T + 1u;
   for (int base = tid; base < total; base += 8 * DT_CELLS) {
     double v[8];
+    int so[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int idx = base + u * DT_CELLS;
-      v[u] = idx < total ? src[idx] : 0.0;
+      const int cell = (int)__umulhi((unsigned)idx, rcpT), t = idx - cell * T;
+      so[u] = cell * ld + t;
+      v[u] = idx < total ? src[cell * Tstride + t] : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * DT_CELLS;
-      if (idx < total) sm[idx + (idx / Tstride) * pad] = v[u];
-    }
+    for (int u = 0; u < 8; ++u)
+      if (base + u * DT_CELLS < total) sm[so[u]] = v[u];
   }
   __syncthreads();
   if (tid < nc) {
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(DT_CELLS) k_detrend_cells(
       flag = 0;
       if (trend) { trend[((size_t)b * C + c) * 2] = sie_nan(); trend[((size_t)b * C + c) * 2 + 1] = sie_nan(); }
       if (do_detrend) {
-        for (int t = 0; t < Tstride; ++t) y[t] = sie_nan();
+        for (int t = 0; t < T; ++t) y[t] = sie_nan();
       } else if (n_nan < T) {
         // pass-through mode keeps a partially-NaN series visible: it is a node whose correlations are NaN
         // (np.nanmax ignores the NaNs, np.corrcoef does not) -- ComplexNetworks.py:32-34
@@ -98,7 +101,6 @@ __global__ void __launch_bounds__(DT_CELLS) k_detrend_cells(
           y[t] = r;
           mx = fmax(mx, r);
         }
-        for (int t = T; t < Tstride; ++t) y[t] = 0.0;
         if (trend) {
           trend[((size_t)b * C + c) * 2] = slope;
           trend[((size_t)b * C + c) * 2 + 1] = icpt;
@@ -112,18 +114,20 @@ __global__ void __launch_bounds__(DT_CELLS) k_detrend_cells(
   }
   if (!do_detrend) return;
   __syncthreads();
+  // residuals back: the window only (samples T.. of dt are never consumed: K1's z rows, K6 and the host read [0, T))
   for (int base = tid; base < total; base += 8 * DT_CELLS) {
     double v[8];
+    int go[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int idx = base + u * DT_CELLS;
-      v[u] = idx < total ? sm[idx + (idx / Tstride) * pad] : 0.0;
+      const int cell = (int)__umulhi((unsigned)idx, rcpT), t = idx - cell * T;
+      go[u] = cell * Tstride + t;
+      v[u] = idx < total ? sm[cell * ld + t] : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * DT_CELLS;
-      if (idx < total) dst[idx] = v[u];
-    }
+    for (int u = 0; u < 8; ++u)
+      if (base + u * DT_CELLS < total) dst[go[u]] = v[u];
   }
 }
 

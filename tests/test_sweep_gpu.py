@@ -132,6 +132,52 @@ def test_multi_init_north_sweep_matches_oracle(lib_built):
     assert n_ok >= 30 and n_fail >= 1 and n_ok + n_fail == 48
 
 
+def test_time_varying_nan_mask_matches_oracle_and_capacity_failures_raise(lib_built):
+    """A cell whose only NaN lies in a late year (data gap, mask change) is a node in the short windows and not in the
+    long ones (`detrend` works on the prefix, north/retrospective_forecasts/September1st_retro.py:178-195): the node
+    capacity must cover the largest window-specific node count, and the domains / forecasts must match the oracle for
+    every window.  A build that exceeds a capacity must raise instead of returning NaN forecasts that look like a
+    reference failure."""
+    from seaiceextentforecasting_b200 import _lib
+    from seaiceextentforecasting_b200.forecast import RetrospectiveSweep
+    fmin, fmax = 1992, 1996
+    Tfull = fmax - 1979 + 1
+    f, _ = syn.make_field(15, 15, Tfull, 411, n_modes=50, noise=0.5, blob=(1.0, 2.5))
+    f = f.copy()
+    ocean = np.argwhere(~np.isnan(f).any(axis=2))
+    rng = np.random.default_rng(5)
+    pick = ocean[rng.choice(len(ocean), 12, replace=False)]
+    for q, (i, j) in enumerate(pick):
+        f[i, j, Tfull - 1 - (q % 3)] = np.nan          # NaN in one of the last three years only
+    name = "north_september"
+    cfg = CONFIGS[name]
+    sie = dict(zip(cfg.regions, syn.make_sie(np.nan_to_num(f), Tfull, 411)))
+    psar = syn.make_psar(15, 15)
+    sw = RetrospectiveSweep([name], {name: f}, sie, fmin, fmax, psar)
+    out = sw.run()
+    n_nodes = sw.sic.n_nodes.cpu().numpy()
+    assert len(set(n_nodes.tolist())) > 1                      # the windows really have different node sets
+    ora = oracle_sweep([cfg], {name: f}, sie, fmin, fmax, psar)[name]
+    for (st, V), (ci, ny) in zip(sw.sic.areas_to_host(), sw.plan.jobs):
+        assert st == 0 and V == ora["V"][ny], ny
+    for k, reg in enumerate(cfg.regions):
+        for i, year in enumerate(sw.years):
+            rec = sw.raw[sw.plan.prob_meta.index((0, k, year))]
+            if ora[reg + "_failed"][i] is not None:
+                assert rec["info"] == -1
+                continue
+            assert rec["info"] == 0
+            t = gp_tol(rec, ora[reg + "_cond"][i])
+            rf, rv = ora[reg + "_fmean"][i], ora[reg + "_fvar"][i]
+            scale = max(abs(rf), np.sqrt(abs(rv)))
+            assert abs(out[name][reg + "_raw_fmean"][i] - rf) <= t * scale, (reg, year, rec, rf)
+            assert abs(out[name][reg + "_raw_fvar"][i] - rv) <= t * max(abs(rv), scale ** 2), (reg, year)
+    # area capacity exceeded -> loud failure, not NaN records
+    small = RetrospectiveSweep([name], {name: f}, sie, fmin, fmax, psar, max_areas=2)
+    with pytest.raises(_lib.SieError):
+        small.run()
+
+
 def test_sweep_hyper_grid_contains_the_script_settings(lib_built):
     """configs[4]: the whole sweep on the 20 x 20 hyper-parameter grid.  The scripts' own (l, sigma) settings are grid
     points (`ls[16], ss[1]` ... north/June1st.py:210-213), so those grid entries must reproduce the forecasts."""
