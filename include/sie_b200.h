@@ -58,7 +58,8 @@ int sie_device_info(int* sm_count, int* max_smem_optin, size_t* l2_bytes);
  * trend       [B][C][2] slope,intercept (NaN for cells with any NaN) or NULL
  * z           [B][ldn][Tp]  unit-norm centred rows, node-compacted, zero padded to Tp (Tp%4==0)
  * node_cell   [B][ldn], cell_node [B][C] (-1 = not a node), n_nodes [B], first_nan_cell [B] (-1 none)
- * status      [B] SIE_JOB_CAPACITY if n_nodes > ldn
+ * status      [B] SIE_JOB_CAPACITY if n_nodes > ldn (ldn: node capacity, a multiple of 4; K2 needs a multiple of 128);
+ *             dt is defined for the window [0, T_b) of every series only
  * B <= 65535 jobs per call; Tp <= ~195 (128 series of Tp+1 doubles are staged in shared memory)
  */
 int sie_detrend_zscore(const double* fields, const int32_t* job_field, const int32_t* job_T,

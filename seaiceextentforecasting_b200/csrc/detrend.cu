@@ -178,42 +178,68 @@ __global__ void __launch_bounds__(1024) k_compact_nodes(int C, int ldn, int32_t*
   }
 }
 
-// One warp per node: centre, scale to unit norm (np.corrcoef's (x-mean)/sqrt(sum (x-mean)^2)), pad with 0.
+// Centre and scale every node series to unit norm (np.corrcoef's (x-mean)/sqrt(sum (x-mean)^2)), pad with 0.
+// One warp per ZR_NODES consecutive nodes: the (short) series of all of them are in flight before the first reduction
+// (a warp per node had 2 loads in flight and 10 dependent shuffles: latency-bound at 25 % of the HBM roof); the
+// arithmetic per node - lane t holds samples t and t+32, xor-butterfly sums - is unchanged.
+constexpr int ZR_NODES = 4;
 __global__ void __launch_bounds__(256) k_zrows(const double* __restrict__ dt, const int32_t* __restrict__ job_T,
                                                const int32_t* __restrict__ node_cell,
                                                const int32_t* __restrict__ n_nodes, int B, int C, int Tstride,
                                                int Tp, int ldn, double* __restrict__ z) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (warp >= (long long)B * ldn) return;
-  const int b = (int)(warp / ldn);
-  const int n = (int)(warp - (long long)b * ldn);
-  double* zr = z + ((size_t)b * ldn + n) * Tp;
+  const int per_job = ldn / ZR_NODES;                       // ldn is a multiple of 128
+  if (warp >= (long long)B * per_job) return;
+  const int b = (int)(warp / per_job);
+  const int n0 = (int)(warp - (long long)b * per_job) * ZR_NODES;
   const int N = min(n_nodes[b], ldn);
-  if (n >= N) {
-    for (int t = lane; t < Tp; t += 32) zr[t] = 0.0;   // rows past N are zero so padded tiles are harmless
-    return;
-  }
   const int T = job_T[b];
-  const double* src = dt + ((size_t)b * C + node_cell[(size_t)b * ldn + n]) * Tstride;
+  double* zr0 = z + ((size_t)b * ldn + n0) * Tp;
   if (T <= 64) {
-    // the whole series sits in two registers per lane: one pass over memory, same summation order as the loops below
-    const double v0 = lane < T ? src[lane] : 0.0, v1 = lane + 32 < T ? src[lane + 32] : 0.0;
-    const double mean = warp_sum((0.0 + v0) + v1) / (double)T;
-    const double d0 = lane < T ? v0 - mean : 0.0, d1 = lane + 32 < T ? v1 - mean : 0.0;
-    const double inv = 1.0 / sqrt(warp_sum(fma(d1, d1, fma(d0, d0, 0.0))));   // q += d*d contracts to an FMA in the loop form
-    if (lane < Tp) zr[lane] = lane < T ? d0 * inv : 0.0;
-    if (lane + 32 < Tp) zr[lane + 32] = lane + 32 < T ? d1 * inv : 0.0;
-    for (int t = lane + 64; t < Tp; t += 32) zr[t] = 0.0;
+    // the whole series sits in two registers per lane: one pass over memory
+    double v0[ZR_NODES], v1[ZR_NODES];
+    int cell[ZR_NODES];
+#pragma unroll
+    for (int u = 0; u < ZR_NODES; ++u) cell[u] = (n0 + u < N) ? node_cell[(size_t)b * ldn + n0 + u] : -1;
+#pragma unroll
+    for (int u = 0; u < ZR_NODES; ++u) {
+      const double* src = dt + ((size_t)b * C + max(cell[u], 0)) * Tstride;
+      v0[u] = (cell[u] >= 0 && lane < T) ? src[lane] : 0.0;
+      v1[u] = (cell[u] >= 0 && lane + 32 < T) ? src[lane + 32] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < ZR_NODES; ++u) {
+      double* zr = zr0 + (size_t)u * Tp;
+      if (cell[u] < 0) {                                    // rows past N are zero so padded tiles are harmless
+        for (int t = lane; t < Tp; t += 32) zr[t] = 0.0;
+        continue;
+      }
+      const double mean = warp_sum((0.0 + v0[u]) + v1[u]) / (double)T;
+      const double d0 = lane < T ? v0[u] - mean : 0.0, d1 = lane + 32 < T ? v1[u] - mean : 0.0;
+      const double inv = 1.0 / sqrt(warp_sum(fma(d1, d1, fma(d0, d0, 0.0))));   // q += d*d contracts to an FMA in the loop form
+      if (lane < Tp) zr[lane] = lane < T ? d0 * inv : 0.0;
+      if (lane + 32 < Tp) zr[lane + 32] = lane + 32 < T ? d1 * inv : 0.0;
+      for (int t = lane + 64; t < Tp; t += 32) zr[t] = 0.0;
+    }
     return;
   }
-  double s = 0.0;
-  for (int t = lane; t < T; t += 32) s += src[t];
-  const double mean = warp_sum(s) / (double)T;
-  double q = 0.0;
-  for (int t = lane; t < T; t += 32) { double d = src[t] - mean; q += d * d; }
-  const double inv = 1.0 / sqrt(warp_sum(q));
-  for (int t = lane; t < Tp; t += 32) zr[t] = (t < T) ? (src[t] - mean) * inv : 0.0;
+  for (int u = 0; u < ZR_NODES; ++u) {
+    const int n = n0 + u;
+    double* zr = zr0 + (size_t)u * Tp;
+    if (n >= N) {
+      for (int t = lane; t < Tp; t += 32) zr[t] = 0.0;
+      continue;
+    }
+    const double* src = dt + ((size_t)b * C + node_cell[(size_t)b * ldn + n]) * Tstride;
+    double s = 0.0;
+    for (int t = lane; t < T; t += 32) s += src[t];
+    const double mean = warp_sum(s) / (double)T;
+    double q = 0.0;
+    for (int t = lane; t < T; t += 32) { double d = src[t] - mean; q += d * d; }
+    const double inv = 1.0 / sqrt(warp_sum(q));
+    for (int t = lane; t < Tp; t += 32) zr[t] = (t < T) ? (src[t] - mean) * inv : 0.0;
+  }
 }
 
 }  // namespace
@@ -241,7 +267,8 @@ extern "C" int sie_detrend_zscore(const double* fields, const int32_t* job_field
   SIE_CHECK_LAUNCH();
   k_compact_nodes<<<B, 1024, 0, st>>>(C, ldn, cell_node, node_cell, n_nodes, first_nan_cell, status);
   SIE_CHECK_LAUNCH();
-  const long long zwarps = (long long)B * ldn;
+  SIE_CHECK_ARG((ldn % ZR_NODES) == 0, "ldn must be a multiple of 4");
+  const long long zwarps = (long long)B * (ldn / ZR_NODES);
   const int wpb = 8;
   k_zrows<<<(unsigned)((zwarps + wpb - 1) / wpb), wpb * 32, 0, st>>>(dt, job_T, node_cell, n_nodes, B, C,
                                                                       Tstride, Tp, ldn, z);
