@@ -712,6 +712,8 @@ k_corr_tma(const double* __restrict__ z, const long long* __restrict__ prefix, c
     const long long item = item_of(k);
     const int b = e0.x, bi = e0.y, bj = e0.z, N = e0.w, ksteps = e1.x;
     const long long rcb = (long long)(((unsigned long long)(unsigned)e1.w << 32) | (unsigned)e1.z);
+    // `R >= 0 && R > rc` as one compare: rc >= 0 -> R > rc; rc < 0 (image -1) -> R > -denorm_min (R >= 0)
+    const double rcd = rcb < 0 ? -4.9406564584124654e-324 : __longlong_as_double(rcb);
     const double* pa = sA + (size_t)e1.y * a_elems + (size_t)(wr * 32 + r8) * Tp + c4;
     const double* pb = sB + (size_t)s * b_elems + (size_t)(wc * 16 + r8) * Tp + c4;
 
@@ -740,64 +742,18 @@ k_corr_tma(const double* __restrict__ z, const long long* __restrict__ prefix, c
     const bool interior = dk >= 2 && row0 + TILE <= N && col0 + TILE_N <= N;
     double lsum = 0.0;
     int lcnt = 0;
-    {   // clip to [-1, 1] (np.clip keeps NaN): ONE branch per tile on the largest |high word| instead of one per value
-      unsigned hmax = 0u;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) hmax = max(hmax, (unsigned)__double2hiint(acc[i][j][h]) & 0x7fffffffu);
-      if (hmax >= 0x3ff00000u) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 2; ++j) { acc[i][j][0] = clip_unit(acc[i][j][0]); acc[i][j][1] = clip_unit(acc[i][j][1]); }
-      }
-    }
-    if (interior) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const double v0 = acc[i][j][0], v1 = acc[i][j][1];
-          const long long i0 = __double_as_longlong(v0), i1 = __double_as_longlong(v1);
-          const bool t0 = i0 > rcb && i0 <= kOneBits, t1 = i1 > rcb && i1 <= kOneBits;   // NaN images lie above 1.0's
-          lsum += t0 ? v0 : 0.0;                                   // adding +0.0 leaves a non-negative sum unchanged
-          lsum += t1 ? v1 : 0.0;
-          lcnt += (int)t0 + (int)t1;
-        }
-    } else {
-      // tiles of the diagonal block and of the ragged edge: count strictly above the diagonal, NaN on it
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int gi = row0 + wr * 32 + i * 8 + r8;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int gj = col0 + wc * 16 + j * 8 + 2 * c4;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const double v = acc[i][j][h];
-            const bool up = gi < N && gj + h < N && (dk >= 2 || gj + h > gi);
-            const long long iv = __double_as_longlong(v);
-            const bool t = up && iv > rcb && iv <= kOneBits;
-            lsum += t ? v : 0.0;
-            lcnt += (int)t;
-            if (dk < 2 && gj + h == gi) acc[i][j][h] = sie_nan();
-          }
-        }
-      }
-    }
     // ---- the sub-tile leaves through the TMA engine (skipped when it lies strictly below the diagonal or outside N)
     const int sr0 = row0 + wr * 32, sc0 = col0 + wc * 16;
-    if (sc0 + TM_BOX_C - 1 >= sr0 && sr0 < N && sc0 < N) {
+    const bool stored = sc0 + TM_BOX_C - 1 >= sr0 && sr0 < N && sc0 < N;
+    auto stage_store = [&](const double (&v)[4][2][2]) {
+      if (!stored) return;
       if (lane == 0 && pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
       const bool odd = r8 & 1;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         double* rowp = box + (size_t)(i * 8 + r8) * TM_BOX_C + 2 * c4;
-        const double2 left = make_double2(acc[i][0][0], acc[i][0][1]), right = make_double2(acc[i][1][0], acc[i][1][1]);
+        const double2 left = make_double2(v[i][0][0], v[i][0][1]), right = make_double2(v[i][1][0], v[i][1][1]);
         // even rows: left block then right block; odd rows the other way round (bank-conflict free wavefronts)
         *reinterpret_cast<double2*>(rowp + (odd ? 8 : 0)) = odd ? right : left;
         *reinterpret_cast<double2*>(rowp + (odd ? 0 : 8)) = odd ? left : right;
@@ -809,14 +765,60 @@ k_corr_tma(const double* __restrict__ z, const long long* __restrict__ prefix, c
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         pending = true;
       }
+    };
+    // clip to [-1, 1] (np.clip keeps NaN): ONE test per tile on the largest |high word| instead of one per value
+    unsigned hmax = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) hmax = max(hmax, (unsigned)__double2hiint(acc[i][j][h]) & 0x7fffffffu);
+    if (interior && hmax < 0x3ff00000u) {
+      // the common case touches the accumulators read-only (a conditional in-place clip / NaN diagonal makes the compiler
+      // copy all 32 accumulator registers on this path too; the epilogue is what bounds this kernel)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double v0 = acc[i][j][0], v1 = acc[i][j][1];
+          // one FP64 compare per value (NaN compares false) and predicated adds: a third of the instructions of the
+          // integer-image test of k_corr_rows; this kernel's epilogue is issue-bound, not FP64-pipe-bound
+          const bool t0 = v0 > rcd, t1 = v1 > rcd;
+          lsum += t0 ? v0 : 0.0;                                   // adding +0.0 leaves a non-negative sum unchanged
+          lsum += t1 ? v1 : 0.0;
+          lcnt += (int)t0 + (int)t1;
+        }
+      stage_store(acc);
+    } else {
+      // tiles of the diagonal block and of the ragged edge, or a value that needs clipping: count strictly above the
+      // diagonal, NaN on it
+      double cv[4][2][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gi = row0 + wr * 32 + i * 8 + r8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int gj = col0 + wc * 16 + j * 8 + 2 * c4;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double v = clip_unit(acc[i][j][h]);
+            const bool up = gi < N && gj + h < N && (dk >= 2 || gj + h > gi);
+            const bool t = up && v > rcd;
+            lsum += t ? v : 0.0;
+            lcnt += (int)t;
+            cv[i][j][h] = (dk < 2 && gj + h == gi) ? sie_nan() : v;
+          }
+        }
+      }
+      stage_store(cv);
     }
-    double lc = (double)lcnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-      lc += __shfl_xor_sync(0xffffffffu, lc, o);
+      lcnt += __shfl_xor_sync(0xffffffffu, lcnt, o);                 // the count stays an integer until it is stored
     }
-    if (lane == 0) *reinterpret_cast<double2*>(parts + (item * TM_CWARPS + warp) * 2) = make_double2(lsum, lc);
+    if (lane == 0) *reinterpret_cast<double2*>(parts + (item * TM_CWARPS + warp) * 2) = make_double2(lsum, (double)lcnt);
   }
   if (lane == 0 && pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores done before the CTA exits
 }

@@ -83,7 +83,10 @@ def tau_only():
 def tma_only():
     """time the stored-R default alone on the 4-member sweep shape (chunk / ring depth tuning in a SIE_TUNE build)"""
     X = Y = 57
-    Ts = sorted([7 + i % 36 for i in range(576)], reverse=True); B = len(Ts); T = max(Ts); C = X * Y
+    Ts = sorted([7 + i % 36 for i in range(576)], reverse=True)
+    if len(sys.argv) > 2:
+        Ts = [int(sys.argv[2])] * 288                 # uniform window: where the kernel sits against each roof
+    B = len(Ts); T = max(Ts); C = X * Y
     data, _ = syn.make_field(X, Y, T, 11)
     n_upper = int((~np.isnan(data).all(axis=2)).sum())
     eng = NetworkBatch(X, Y, T, B, latlon=False, n_upper=n_upper, keep_R=True, max_areas=8)
@@ -92,7 +95,9 @@ def tma_only():
     rc = h2d(np.array([r_crit_ttest(t, 0.01) for t in Ts]))
     eng.detrend_zscore(fields, jf, jT, True); torch.cuda.synchronize()
     ms = timed(lambda: eng.corr_tau(rc, store_R=True, kernel=_lib.SIE_CORR_TMA))
-    print(f"tma chunk={os.environ.get('SIE_TM_CHUNK')} S={os.environ.get('SIE_TM_S')}: {ms:.3f} ms")
+    N = eng.n_nodes.cpu().numpy().astype(np.float64)
+    flop = float((N * (N + 1.0) * np.asarray(Ts, dtype=np.float64)).sum()); byts = float((4.0 * N * N).sum())
+    print(f"tma B={B} T={min(Ts)}..{max(Ts)}: {ms:.3f} ms  {flop / ms / 1e9:.1f} TFLOP/s  {byts / ms / 1e6:.0f} GB/s stored")
 
 
 if __name__ == "__main__":
