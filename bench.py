@@ -360,6 +360,12 @@ def roofline_table(sw, stage_ms, hbm_peak, hbm_src, fp64_peak):
             roof[tag + ".corr_tau"] = {"bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
                                        "frac": ach / fp64_peak, "traffic": None, "ms": ms, "peak_source": fp64_src,
                                        "store_GBps": float((4.0 * N * N).sum()) / (ms * 1e-3) / 1e9,
+                                       # the launch mixes windows on both sides of the ridge (T ~ 22): per network the
+                                       # binding roof is max(flop / tensor peak, stored bytes / HBM peak)
+                                       "two_roof_ideal_ms": float(np.maximum(N * (N + 1.0) * T / (fp64_peak * 1e12),
+                                                                             4.0 * N * N / (hbm_peak * 1e9)).sum() * 1e3),
+                                       "frac_two_roofs": float(np.maximum(N * (N + 1.0) * T / (fp64_peak * 1e12),
+                                                                          4.0 * N * N / (hbm_peak * 1e9)).sum() * 1e3) / ms,
                                        "model": "N(N+1)T flop per network (upper triangle) on the FP64 tensor pipe (DMMA); "
                                                 "4 N^2 bytes stored (upper triangle of R) + 8 N Tp read"}
         hbm(tag + ".area_level", 8.0 * float(eng.area_work.cpu().numpy()[:, 0].sum()),
