@@ -88,6 +88,73 @@ def test_mlii_matches_oracle(lib_built, seed):
     np.testing.assert_allclose(g, og_, rtol=1e-7, atol=1e-9 * max(1.0, np.abs(og_).max()))
 
 
+import glob
+import os
+
+_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+_SWEEPS = sorted(glob.glob(os.path.join(_GOLD, "sweep_*.npz")))
+
+
+@pytest.mark.parametrize("path", _SWEEPS, ids=[os.path.basename(p) for p in _SWEEPS])
+def test_mlii_matches_reference_golden(lib_built, path):
+    """The device `MLII` against the value and gradient the UNMODIFIED reference scripts' nested MLII() returned for the
+    last target year of each golden sweep (tests/golden/make_golden.py lifts it out of the seven retrospective scripts):
+    the problem is rebuilt exactly like tests/test_oracle_golden.py::test_mlii_oracle_equals_reference does."""
+    from oracle import gp as ogp
+    from oracle import sweep as osweep
+    from seaiceextentforecasting_b200.forecast import forecast, mlii
+    g = np.load(path)
+    name = os.path.basename(path)[len("sweep_"):-len(".npz")]
+    cfg = CONFIGS[name]
+    fmin, fmax = int(g["fmin"]), int(g["fmax"])
+    year = fmax
+    ny = year - 1 if cfg.prev_year_network else year
+    _, anoms, _ = osweep.build_network(g["sic"], ny, False, g["psar"])
+    sst_anoms = None
+    if cfg.use_sst:
+        _, sst_anoms, _ = osweep.build_network(g["sst"], year, True, g["sst_lat"])
+    row = year - (fmin - 1) - 1
+    sdt = g["siedt_" + cfg.regions[0]]
+    y = sdt[row, 1:year - 1979] if cfg.prev_year_network else sdt[row, 0:year - 1979]
+    theta = np.asarray(g["mlii_theta"], dtype=np.float64)
+    nl, grad = mlii(theta, y, anoms, sst_anoms, rule=cfg.rule[0], alpha=cfg.alpha, zscore=cfg.zscore)
+    ref_nl, ref_grad = float(g["mlii_nl"]), np.asarray(g["mlii_grad"], dtype=np.float64)
+    if not np.isfinite(ref_nl):
+        assert nl == np.inf and np.isinf(grad).all()
+        return
+    # conditioning of this problem (same widening terms as the forecasts, module docstring)
+    rec = forecast(y, anoms, sst_anoms, rule=cfg.rule[0], alpha=cfg.alpha, zscore=cfg.zscore, ell=float(np.exp(theta[0])),
+                   sig=float(np.exp(theta[1])))
+    rule = {RULE_POS: "pos", RULE_ALL: "all", RULE_POS_SIG: "pos_sig"}[cfg.rule[0]]
+    X, Xs, M = ogp.design(ogp.select_predictors(y, anoms, sst_anoms, rule, cfg.alpha), cfg.zscore)
+    from scipy.linalg import expm
+    K = X @ expm(float(np.exp(theta[0])) * M) @ X.T + float(np.exp(theta[1])) * np.eye(len(y))
+    t = tol(rec, np.linalg.cond(K))
+    n = len(y)
+    assert abs(nl - ref_nl) <= t * max(1.0, abs(ref_nl), 1.5 * n), (nl, ref_nl, t)
+    # each gradient component is trace(K^-1 dK)/2 - a^T dK a/2 (north/June1st.py:248-252): a difference of two terms that
+    # are larger than the result, and dK/dl = X (M Sigma) X^T + sn I is itself a product with heavy cancellation (M has
+    # zero column sums, ||M||_1 ~ 1e6, |X| ~ 1e3 on these inputs).  The bound is the conditioning-aware one, relative to
+    # the sum of the two terms' magnitudes, or -- where the reference's OWN result is less stable than that -- four
+    # times the spread of the reference formula under 1-ulp relative perturbations of M (its own sensitivity, the
+    # argument tests/test_expm_spec.py makes for expm).
+    yv = np.asarray(y, dtype=np.float64)[:, None]
+    ell_v, sig_v = float(np.exp(theta[0])), float(np.exp(theta[1]))
+    St = expm(ell_v * M)
+    Lt = np.linalg.cholesky(X @ St @ X.T + np.eye(n) * sig_v)
+    sf = float((yv.T @ np.linalg.solve(Lt.T, np.linalg.solve(Lt, yv)))[0, 0] / n)
+    S = sf * St
+    Kf = X @ S @ X.T + np.eye(n) * sf * sig_v
+    a = np.linalg.solve(Kf, yv)
+    rng = np.random.default_rng(0)
+    pert = np.array([ogp.mlii(theta, X, yv, M * (1.0 + 2.0 ** -52 * rng.standard_normal(M.shape)))[1] for _ in range(6)])
+    spread = np.abs(pert - ref_grad[None, :]).max(axis=0)
+    for gi, dK in enumerate((X @ (M @ S) @ X.T + np.eye(n) * sf * sig_v, X @ S @ X.T + np.eye(n) * sf)):
+        mag = abs(np.trace(np.linalg.solve(Kf, dK))) / 2 + abs(float((a.T @ dK @ a)[0, 0])) / 2
+        bound = max(1e-7 * abs(ref_grad[gi]), t * max(1.0, mag), 4.0 * spread[gi])
+        assert abs(grad[gi] - ref_grad[gi]) <= bound, (gi, grad, ref_grad, t, mag, spread)
+
+
 def test_not_spd_reports_like_reference(lib_built):
     """sigma_n~ = 0 with more rows than predictors: K is singular -> LinAlgError in forecast(), inf in MLII."""
     from seaiceextentforecasting_b200.forecast import forecast, mlii
