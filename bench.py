@@ -605,7 +605,7 @@ def run_ours(args):
             "roofline": main_roof,
             "roofline_all": roof,
             "schedule": waves_desc + "; domain growth = persistent grid popping jobs longest-window-first; stage_ms / "
-                        "roofline timed in a separate pass with every stage alone on the GPU; e2e loop = RetrospectiveSweep.run_many (step i's "
+                        "roofline timed in a separate pass with every stage alone on the GPU; e2e loop = RetrospectiveSweep.run_many (step i+1's H2D on a copy stream into a second input buffer while step i computes; step i's "
                         "D2H + host assemble overlap step i+1)",
             "corr_25km": corr25,
             "strong_scaling": strong,

@@ -716,8 +716,9 @@ class RetrospectiveSweep:
         """Generator over `n` sweeps run back to back (a perturbed-input ensemble, bench.py's end-to-end loop): every
         step does its own host -> device copy of the inputs, the whole hot path and a device -> host read of its results,
         but step i's read lands in a pinned buffer and is assembled on the host while step i+1 is already on the
-        device, so host work (launch enqueue, assemble) is off the device's critical path.  Yields the same dict as
-        run() per step; `self.raw` holds the records of the step just yielded."""
+        device, so host work (launch enqueue, assemble) is off the device's critical path, and step i+1's inputs are
+        copied from the pinned buffers into a second set of device buffers on a copy stream while step i computes.
+        Yields the same dict as run() per step; `self.raw` holds the records of the step just yielded."""
         if getattr(self, "_pin_out", None) is None:
             self._pin_out = [torch.empty(self.gp.out.numel(), dtype=torch.uint8).pin_memory() for _ in range(2)]
         pending = None
@@ -729,9 +730,48 @@ class RetrospectiveSweep:
                 self.check_status(self.raw)
             return self.plan.assemble(self.raw)
 
-        for i in range(int(n)):
-            self.upload()
-            self.compute()
+        # inputs are double-buffered on the device: step i+1's host -> device copy runs on a copy stream while step i
+        # computes (with CUDA-graph replay the captured step reads fixed addresses: single buffer, copy in stream order)
+        n = int(n)
+        overlap = not self.use_graph
+        if overlap:
+            if getattr(self, "dev", None) is None:
+                self.dev = {k: torch.empty_like(t, device="cuda") for k, t in self._pin.items()}
+            if getattr(self, "_dev2", None) is None:
+                self._dev2 = {k: torch.empty_like(t, device="cuda") for k, t in self._pin.items()}
+                self._copy_stream = torch.cuda.Stream()
+            devs = [self.dev, self._dev2]
+            main = torch.cuda.current_stream()
+            up_ev, done_ev = [None, None], [None, None]
+
+            def upload_to(k):
+                cs = self._copy_stream
+                if done_ev[k] is not None:
+                    cs.wait_event(done_ev[k])           # the step that last read this buffer is finished
+                else:
+                    cs.wait_stream(main)
+                with torch.cuda.stream(cs):
+                    for key, t in self._pin.items():
+                        devs[k][key].copy_(t, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                return ev
+
+            if n > 0:
+                up_ev[0] = upload_to(0)
+        for i in range(n):
+            if overlap:
+                k = i & 1
+                main.wait_event(up_ev[k])
+                self.dev = devs[k]
+                if i + 1 < n:
+                    up_ev[k ^ 1] = upload_to(k ^ 1)
+                self.compute()
+                done_ev[k] = torch.cuda.Event()
+                done_ev[k].record(main)
+            else:
+                self.upload()
+                self.compute()
             buf = self._pin_out[i & 1]
             buf.copy_(self.gp.out, non_blocking=True)
             ev = torch.cuda.Event()
