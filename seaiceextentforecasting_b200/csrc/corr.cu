@@ -777,18 +777,20 @@ k_corr_tma(const double* __restrict__ z, const long long* __restrict__ prefix, c
     if (interior && hmax < 0x3ff00000u) {
       // the common case touches the accumulators read-only (a conditional in-place clip / NaN diagonal makes the compiler
       // copy all 32 accumulator registers on this path too; the epilogue is what bounds this kernel)
-#pragma unroll
+      double ps[4] = {0.0, 0.0, 0.0, 0.0};                          // four independent partial sums: the 16 adds are a
+#pragma unroll                                                     // chain of 4 + 2 dependent FP64 adds instead of 16
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const double v0 = acc[i][j][0], v1 = acc[i][j][1];
-          // one FP64 compare per value (NaN compares false) and predicated adds: a third of the instructions of the
-          // integer-image test of k_corr_rows; this kernel's epilogue is issue-bound, not FP64-pipe-bound
+          // one FP64 compare per value (NaN compares false): a third of the instructions of the integer-image test of
+          // k_corr_rows; this kernel's epilogue is latency / issue-bound, not FP64-pipe-bound
           const bool t0 = v0 > rcd, t1 = v1 > rcd;
-          lsum += t0 ? v0 : 0.0;                                   // adding +0.0 leaves a non-negative sum unchanged
-          lsum += t1 ? v1 : 0.0;
+          ps[i] += t0 ? v0 : 0.0;                                  // adding +0.0 leaves a non-negative sum unchanged
+          ps[i] += t1 ? v1 : 0.0;
           lcnt += (int)t0 + (int)t1;
         }
+      lsum = (ps[0] + ps[1]) + (ps[2] + ps[3]);
       stage_store(acc);
     } else {
       // tiles of the diagonal block and of the ragged edge, or a value that needs clipping: count strictly above the
