@@ -60,7 +60,7 @@ __device__ __forceinline__ double sie_nan() { return __longlong_as_double(0x7ff8
 // that consumes it (the adds) after, so a leaf's gathers are all in flight before the first add instead of being
 // interleaved load-use-load-use (which serialises the memory round trips).
 #ifndef SIE_PW_SMALL_NQ
-#define SIE_PW_SMALL_NQ 4       // unrolled leaf variants: <= 8 * SIE_PW_SMALL_NQ elements and <= 128 (0: only the latter)
+#define SIE_PW_SMALL_NQ 8       // unrolled leaf variants: <= 8 * SIE_PW_SMALL_NQ elements and <= 128 (0: only the latter); 8 measured best of 4..12
 #endif
 template <int NQ> __device__ __forceinline__ void sie_fence_regs(double (&v)[NQ]);
 template <> __device__ __forceinline__ void sie_fence_regs<1>(double (&v)[1]) { asm volatile("" : "+d"(v[0])); }
@@ -69,6 +69,17 @@ template <> __device__ __forceinline__ void sie_fence_regs<4>(double (&v)[4]) {
 }
 template <> __device__ __forceinline__ void sie_fence_regs<8>(double (&v)[8]) {
   asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]), "+d"(v[5]), "+d"(v[6]), "+d"(v[7]));
+}
+template <> __device__ __forceinline__ void sie_fence_regs<6>(double (&v)[6]) {
+  asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]), "+d"(v[5]));
+}
+template <> __device__ __forceinline__ void sie_fence_regs<10>(double (&v)[10]) {
+  asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]), "+d"(v[5]), "+d"(v[6]), "+d"(v[7]),
+                    "+d"(v[8]), "+d"(v[9]));
+}
+template <> __device__ __forceinline__ void sie_fence_regs<12>(double (&v)[12]) {
+  asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]), "+d"(v[5]), "+d"(v[6]), "+d"(v[7]),
+                    "+d"(v[8]), "+d"(v[9]), "+d"(v[10]), "+d"(v[11]));
 }
 template <> __device__ __forceinline__ void sie_fence_regs<16>(double (&v)[16]) {
   asm volatile("" : "+d"(v[0]), "+d"(v[1]), "+d"(v[2]), "+d"(v[3]), "+d"(v[4]), "+d"(v[5]), "+d"(v[6]), "+d"(v[7]),
