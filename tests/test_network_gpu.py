@@ -97,6 +97,22 @@ def test_network_full_north_grid(lib_built):
     assert len(n.V) >= 2
 
 
+@pytest.mark.parametrize("X,Y,T,latlon,seed", [(96, 96, 20, False, 201), (64, 144, 12, True, 202)])
+def test_network_above_8192_cells_32bit_evicted_variant(lib_built, X, Y, T, latlon, seed):
+    """Grids of >= 8192 cells take the <512 threads, 32-bit indices> domain-growth variant with per-cell arrays evicted to
+    global scratch (csrc/area.cu plan_area: the `place` mask) -- the variant the 25 km builds use, here at a size the
+    oracle finishes in ~15 s, on a polar and on a lat-lon (wrapping) grid: bit-exact domains like every other grid."""
+    from oracle.gp import detrend as odetrend
+    assert X * Y >= 8192
+    data, _ = syn.make_field(X, Y, T, seed, latlon=latlon)
+    odt, _ = odetrend(data)
+    kw = {"lat": syn.make_lat_grid(X, Y)} if latlon else {"area": syn.make_psar(X, Y)}
+    n = _product(odt, latlon, kw)
+    o = _oracle(odt, latlon, kw)
+    compare_networks(n, o, odt)
+    assert len(n.V) >= 50
+
+
 def test_network_south_grid(lib_built):
     """81x81 (config 3, south/February1st.py:79): 6561 cells do not fit the all-on-chip layout of k_area_level, so
     this exercises the placement that evicts integer arrays to global scratch."""
