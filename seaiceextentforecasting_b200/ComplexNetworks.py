@@ -22,8 +22,10 @@ from .engine import NetworkBatch, h2d, r_crit_ttest, require_cuda
 
 class Network:
     # Largest correlation matrix (bytes) the class keeps on the device; above it `tau` runs the tau-only correlation
-    # pass and `area_level` recomputes the correlations it needs from the unit-norm rows (a 25 km grid: 32-148 GB).
-    max_matrix_bytes = 24 << 30
+    # pass and `area_level` recomputes the correlations it needs from the unit-norm rows (a 25 km grid: 32-148 GB; the
+    # stored matrix makes domain growth ~10x faster).  None: half of the device memory that is free when the engine is
+    # created (a 63 574-node 25 km network, 32 GB, is stored on a 180-GB B200).
+    max_matrix_bytes = None
 
     def __init__(self, data, V={}, A={}, corrs=[], tau=0, nodes=[], unavail=[], anomaly={}, links={},
                  strength={}, strengthmap=[]):
@@ -49,8 +51,11 @@ class Network:
             data = np.ascontiguousarray(self.data, dtype=np.float64)
             n_upper = int((~np.isnan(data).all(axis=2)).sum())
             ldn = max(128, (n_upper + 127) // 128 * 128)
+            limit = self.max_matrix_bytes
+            if limit is None:
+                limit = torch.cuda.mem_get_info()[0] // 2
             self._eng = NetworkBatch(self.dimX, self.dimY, self.dimT, 1, latlon=False, n_upper=n_upper,
-                                     keep_R=8 * ldn * ldn <= self.max_matrix_bytes)
+                                     keep_R=8 * ldn * ldn <= limit)
             self._fields = h2d(data.reshape(1, self.dimX * self.dimY, self.dimT))
             self._job_field = torch.zeros(1, dtype=torch.int32, device="cuda")
             self._job_T = torch.full((1,), self.dimT, dtype=torch.int32, device="cuda")
