@@ -7,13 +7,14 @@
 // kind, and ptxas splits the larger sm_90 f64 shapes into 8x8x4 on sm_100a).  A 128-row panel of Z is one
 // contiguous 128*Tp*8-byte run, so operands are staged with 1-D bulk async copies (cp.async.bulk -> SASS
 // UBLKCP, the TMA engine) completing on an mbarrier; Tp = 4 (mod 8) makes the fragment loads
-// bank-conflict free without swizzling.  Persistent 256-thread CTAs (two per SM, so one CTA's stores overlap
-// the other's MMAs) walk a precomputed table of 128x64 tiles on or right of the diagonal blocks; only those
-// tiles are computed, and only the UPPER TRIANGLE of R is stored: every reader (K3, K4/K5, the host accessors)
-// addresses R[min(i,j)][max(i,j)], so the matrix is symmetric by construction like numpy's syrk-based corrcoef
-//  and K2 writes 4 N^2 instead of 8 N^2 bytes.  Off-diagonal tiles are staged in shared memory (over
-// the operand panels) and written as whole rows: 512-byte runs.  (k_corr_rows' stored mode still writes the mirror
-// too; it is a superset of what the readers need.)
+// bank-conflict free without swizzling.  Every kernel walks a precomputed table of 128x64 tiles on or right of the
+// diagonal blocks; only those tiles are computed, and only the UPPER TRIANGLE of R is stored: every reader (K3, K4/K5,
+// the host accessors) addresses R[min(i,j)][max(i,j)], so the matrix is symmetric by construction like numpy's
+// syrk-based corrcoef and K2 writes 4 N^2 instead of 8 N^2 bytes.  Three kernels share the table:
+//   k_corr_tma   (default when R is stored) finished sub-tiles leave as tensor-map bulk stores (TMA), see below;
+//   k_corr_rows  (default for the tau-only pass) row-resident A panel, producer warp + 16 consumer warps;
+//   k_corr_tiles (fallback for windows too long for the others' shared memory) persistent 256-thread CTAs, two per SM;
+//                off-diagonal tiles are staged in shared memory (over the operand panels) and written as whole rows.
 // Algorithmic work: N(N+1)T flop per network (upper triangle), 4 N(N+1) bytes if R is stored.
 #include <cuda.h>
 #include "common.cuh"
@@ -988,12 +989,10 @@ extern "C" int sie_corr_tau(const double* z, const int32_t* n_nodes, const int32
   const size_t rw_stage = (size_t)TILE_N * Tp * sizeof(double);
   int S = (size_t)max_optin < rw_fixed + 256 ? 0 : (int)(((size_t)max_optin - 256 - rw_fixed) / rw_stage);
   if (S > RW_MAXS) S = RW_MAXS;
-  // default: rows kernel for the tau-only pass (25.2 vs 22.6 TFLOP/s at 25 km), tile kernel when R is stored (2.14 vs
-  // 2.29 ms on the 144-network sweep: the staged tile's extra trip through the LSU pipe costs what the resident A
-  // panel saves).  `kernel` = SIE_CORR_TILES / SIE_CORR_ROWS overrides (A/B timing, parity tests of both paths).
-  // default: rows kernel for the tau-only pass (25.2 vs 22.6 TFLOP/s at 25 km), tile kernel when R is stored (0.277 vs
-  // 0.325 ms on 24 57x57 networks, tools/corr_ab.py: the rows kernel's staging trip through shared memory costs more
-  // than its resident A panel and its store warps save)
+  // defaults (SIE_CORR_AUTO): rows kernel for the tau-only pass (25.2 vs 22.6 TFLOP/s at 25 km); TMA-store kernel when R is
+  // stored (4.0 ms on 576 57x57 networks against 5.6 ms for the tile kernel and 6.4 ms for the rows kernel's store-warp
+  // mode, tools/corr_ab.py), the tile kernel only when the window is too long for the TMA kernel's shared memory.
+  // `kernel` = SIE_CORR_TILES / _ROWS / _ROWS_MIRROR / _TMA overrides (A/B timing, parity tests of every path).
   // stored R: the TMA-store kernel (tensor-map bulk stores straight from the consumer warps) whenever its shared memory
   // fits: two A panels + the 64-KB store boxes + >= 2 ring stages
   const size_t tm_fixed = 2 * (size_t)TILE * Tp * sizeof(double) + (size_t)TM_CWARPS * TM_BOX_R * TM_BOX_C * sizeof(double);
