@@ -204,6 +204,9 @@ int sie_gp_forecast(const SieGpProblem* prob, int P, const double* y_all,
                     const double* anom_sst, const int32_t* n_areas_sst, int max_areas_sst, int Tstride_sst,
                     int max_pred, SieGpResult* out, void* scratch, size_t scratch_bytes, void* stream);
 size_t sie_gp_scratch_bytes(int P, int max_pred, int max_n);
+/* Profiling aid, not part of the reference-facing interface: reads and clears 16 per-phase SM-cycle counters of the GP kernel
+ * (all zero unless the library was built with -DSIE_GP_TIMERS; tools/gp_phases.py). */
+int sie_debug_gp_phases(unsigned long long* out16);
 
 /* Hyper-parameter grid (the search the reference leaves commented out at north/June1st.py:259-262, done over the
  * `ls` x `ss` grids of :210-211): problem p fixes (network set, region, l = prob[p].ell); Sigma~ = expm(l M) and

@@ -35,6 +35,13 @@ __device__ const double kB13[14] = {64764752532480000., 32382376266240000., 7771
                                     129060195264000., 10559470521600., 670442572800., 33522128640., 1323241920.,
                                     40840800., 960960., 16380., 182., 1.};
 
+// per-phase SM cycles summed over all problems (thread 0 of every CTA; -DSIE_GP_TIMERS builds only; tools/gp_phases.py)
+__device__ unsigned long long g_gp_phase[16];
+#ifdef SIE_GP_TIMERS
+#define GP_TICK(i) do { if (threadIdx.x == 0) { const long long t__ = clock64(); atomicAdd(&g_gp_phase[i], (unsigned long long)(t__ - gp_t_last)); gp_t_last = t__; } } while (0)
+#else
+#define GP_TICK(i) do { } while (0)
+#endif
 constexpr int KC = 16;            // GEMM k-chunk
 constexpr int LDA_S = 20;         // As[64][20]: row stride = 4 (mod 16) doubles -> conflict-free DMMA A fragments
 constexpr int LDB_S = 68;         // Bs[16][68]: same property for B fragments
@@ -380,6 +387,8 @@ __device__ __noinline__ double* cta_expm(double** buf, int ld, int np_, double* 
                             Smem& sm) {
   double* A = buf[1]; double* A2 = buf[2]; double* A4 = buf[3]; double* A6 = buf[4];
   double* B5 = buf[5]; double* B6 = buf[6]; double* B7 = buf[7]; double* B8 = buf[8];
+  long long gp_t_last = clock64();
+  (void)gp_t_last;
   cta_gemm(A2, ld, A, ld, A, ld, np_, np_, np_, sm);
   cta_gemm(A4, ld, A2, ld, A2, ld, np_, np_, np_, sm);
   cta_gemm(A6, ld, A4, ld, A2, ld, np_, np_, np_, sm);
@@ -387,6 +396,7 @@ __device__ __noinline__ double* cta_expm(double** buf, int ld, int np_, double* 
   const double d4 = pow(cta_norm1(A4, ld, np_, sm), 0.25);
   const double d6 = pow(cta_norm1(A6, ld, np_, sm), 1.0 / 6.0);
   const double eta0 = fmax(d4, d6);
+  GP_TICK(1);                               // A^2, A^4, A^6 and their norms
   int m = 0, s = 0;
   if (eta0 < kTheta[0] && ell_of(cta_absnorm_power(A, ld, np_, 1.0, 7, v0, v1, sm), normA, 0, 3) == 0) m = 3;
   if (!m && eta0 < kTheta[1] && ell_of(cta_absnorm_power(A, ld, np_, 1.0, 11, v0, v1, sm), normA, 1, 5) == 0) m = 5;
@@ -398,6 +408,7 @@ __device__ __noinline__ double* cta_expm(double** buf, int ld, int np_, double* 
     if (eta2 < kTheta[2] && ell_of(cta_absnorm_power(A, ld, np_, 1.0, 15, v0, v1, sm), normA, 2, 7) == 0) m = 7;
     if (!m && eta2 < kTheta[3] && ell_of(cta_absnorm_power(A, ld, np_, 1.0, 19, v0, v1, sm), normA, 3, 9) == 0) m = 9;
   }
+  GP_TICK(2);                               // order selection: A^8 and the |A|^p power iterations of orders 3..9
   double* U = B7; double* V = B8;
   if (m == 3) {
     cta_lincomb(B5, ld, np_, kB3[1], A2, kB3[3], nullptr, 0, nullptr, 0, nullptr);
@@ -435,7 +446,9 @@ __device__ __noinline__ double* cta_expm(double** buf, int ld, int np_, double* 
     s = (sv > 0.0) ? (int)sv : 0;
     if (!(sv == sv) || sv > 2000.0) s = 2000;
     const double sc = ldexp(1.0, -s);
+    GP_TICK(2);
     s += ell_of(cta_absnorm_power(A, ld, np_, sc, 27, v0, v1, sm), normA * sc, 4, 13);
+    GP_TICK(3);                             // the 27-step |A|^27 power iteration of order 13
     if (s > 2000) s = 2000;
     const double s1 = ldexp(1.0, -s), s2 = ldexp(1.0, -2 * s), s4 = ldexp(1.0, -4 * s), s6 = ldexp(1.0, -6 * s);
 #pragma unroll 2
@@ -452,6 +465,7 @@ __device__ __noinline__ double* cta_expm(double** buf, int ld, int np_, double* 
     cta_gemm(B6, ld, A6, ld, B5, ld, np_, np_, np_, sm);                                   // V2
     cta_lincomb(V, ld, np_, kB13[0], A6, kB13[6], A4, kB13[4], A2, kB13[2], B6);
   }
+  GP_TICK(4);                               // Pade numerator / denominator (element-wise passes + 1-3 GEMMs)
   // P = V - U -> B5 ; Q = V + U -> B6 ; solve P X = Q
 #pragma unroll 4
   for (int idx = threadIdx.x; idx < np_ * np_; idx += GT) {
@@ -461,11 +475,13 @@ __device__ __noinline__ double* cta_expm(double** buf, int ld, int np_, double* 
   }
   __syncthreads();
   cta_lu_solve(B5, B6, ld, np_, sm);
+  GP_TICK(5);                               // LU solve
   double* Xc = B6; double* Xn = B7;
   for (int it = 0; it < s; ++it) {
     cta_gemm(Xn, ld, Xc, ld, Xc, ld, np_, np_, np_, sm);
     double* t = Xc; Xc = Xn; Xn = t;
   }
+  GP_TICK(6);                               // s squarings
   *m_out = m; *s_out = s;
   return Xc;
 }
@@ -703,6 +719,8 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
     res.n_pred = 0; res.expm_m = 0; res.expm_s = 0; res.info = 0;
     res.cycles_total = 0; res.cycles_expm = 0;
     const long long clk_start = clock64();
+    long long gp_t_last = clk_start;
+    (void)gp_t_last;
     __syncthreads();
     if (n < 2 || n + 1 > MAXN) {
       if (tid == 0) { res.info = -2; for (int k = 0; k < ns; ++k) out[(size_t)p * ns + k] = res; }
@@ -817,10 +835,12 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
     }
     __syncthreads();
     int em = 0, es = 0;
+    GP_TICK(0);                             // selection, design matrix, Laplacian
     const long long clk_e0 = clock64();
     const double* E = cta_expm(buf, ld, np_, v0, v1, &em, &es, sm);
     res.expm_m = em; res.expm_s = es;
     res.cycles_expm = clock64() - clk_e0;
+    gp_t_last = clock64();
     // ---- W = X Sigma~ X^T : XE = X E (n x Np), then W = XE X^T (n x n, shared)
     cta_gemm(XE, ld, Xg, ld, E, ld, n, np_, np_, sm);
     for (int idx = tid; idx < n * n; idx += GT) {
@@ -872,6 +892,7 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
       }
       continue;                                                // next problem (the loop head synchronises the CTA)
     }
+    GP_TICK(7);                             // X E, W = X E X^T (+ gradient operands)
     for (int ks = 0; ks < ns; ++ks) {
     const double sig = sig_grid ? sig_grid[ks] : pr.sig;
     SieGpResult* const outp = out + (size_t)p * ns + ks;
@@ -986,6 +1007,7 @@ k_gp_forecast(const SieGpProblem* __restrict__ prob, int P, const double* __rest
         __syncthreads();
       }
     }
+    GP_TICK(8);                             // two Cholesky factorisations, solves, predictive mean / variance (+ gradient)
     if (tid == 0) { res.cycles_total = clock64() - clk_start; *outp = res; }
     }   // sigma loop
   }
@@ -1033,6 +1055,16 @@ int gp_grid(int P) {
 }
 
 }  // namespace
+
+// Profiling aid (not part of the reference-facing interface): reads and clears the per-phase cycle counters of
+// k_gp_forecast; all zero unless the library was built with -DSIE_GP_TIMERS.
+extern "C" int sie_debug_gp_phases(unsigned long long* out16) {
+  if (!out16) return SIE_ERR_ARG;
+  if (cudaMemcpyFromSymbol(out16, g_gp_phase, sizeof(unsigned long long) * 16) != cudaSuccess) return SIE_ERR_LAUNCH;
+  unsigned long long zero[16] = {0};
+  if (cudaMemcpyToSymbol(g_gp_phase, zero, sizeof(zero)) != cudaSuccess) return SIE_ERR_LAUNCH;
+  return SIE_OK;
+}
 
 extern "C" size_t sie_gp_scratch_bytes(int P, int max_pred, int max_n) {
   (void)max_n;
