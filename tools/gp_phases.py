@@ -25,8 +25,6 @@ sw.upload()
 sw.compute(waves=0)
 torch.cuda.synchronize()
 lib = _lib.load()
-lib.sie_debug_gp_phases.restype = C.c_int
-lib.sie_debug_gp_phases.argtypes = [C.POINTER(C.c_ulonglong)]
 buf = (C.c_ulonglong * 16)()
 lib.sie_debug_gp_phases(buf)                    # clear
 sw.compute(waves=0)
