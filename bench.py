@@ -521,8 +521,8 @@ def run_ours(args):
     value = total_forecasts / (ms_per_step * 1e-3)
 
     # ---------------- end to end through the public API: pinned host -> device, compute, device -> host
-    for _ in range(2):
-        sw.run()
+    for out in sw.run_many(max(2, min(args.warmup, 3))):     # warm-up through the same loop: its second input buffer set,
+        pass                                                 # copy stream and pinned result buffers are created once
     sync_all()
     t0 = time.perf_counter()
     for out in sw.run_many(args.steps):      # every step: H2D of its inputs, the hot path, D2H of its results; the host
